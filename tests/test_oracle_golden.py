@@ -1,0 +1,130 @@
+"""CPU: the oracle restatement (oracle/gnnml3_oracle.py) against fixtures produced by the UNMODIFIED
+reference (oracle/make_golden.py).  This is what pins the oracle (task section 3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnnml3_oracle as O
+from conftest import GOLDEN, load_npz
+
+SD_Z, SD_META = load_npz("spectral_design.npz")
+CV_Z, CV_META = load_npz("spect_conv.npz")
+
+
+@pytest.mark.parametrize("case", SD_META, ids=[c["name"] for c in SD_META])
+def test_spectral_design_matches_reference(case):
+    n = case["name"]
+    with np.errstate(all="ignore"):
+        o = O.spectral_design(SD_Z[n + "/ei"], SD_Z[n + "/x"], **case["kw"])
+    # edge indexing: bit-exact
+    assert np.array_equal(o["edge_index2"], SD_Z[n + "/ei2"])
+    assert o["edge_index2"].dtype == np.int64
+    assert np.array_equal(o["x"], SD_Z[n + "/ox"])
+    # same LAPACK, same numpy: values agree to float32 round-off (compared as matrices)
+    nn = SD_Z[n + "/x"].shape[0]
+    a = O.supports_dense(o["edge_index2"], o["edge_attr2"], nn)
+    b = O.supports_dense(SD_Z[n + "/ei2"], SD_Z[n + "/ea2"], nn)
+    np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(o["lmax"], SD_Z[n + "/lmax"], rtol=1e-6)
+
+
+def _params(z, n):
+    pre = n + "/p/"
+    return {k[len(pre):]: torch.tensor(z[k]) for k in z.files if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("case", [c for c in CV_META if c["kind"] == "conv"], ids=lambda c: c["name"])
+def test_spectconv_matches_reference(case):
+    n = case["name"]
+    p = {k: v.requires_grad_(True) for k, v in _params(CV_Z, n).items()}
+    x = torch.tensor(CV_Z[n + "/x"], requires_grad=True)
+    ea = torch.tensor(CV_Z[n + "/ea"], requires_grad=True)
+    ei = torch.tensor(CV_Z[n + "/ei"])
+    kw = case["kw"]
+    out = O.spectconv_forward(x, ei, ea, p["weight"], p.get("bias"), selfconn=kw.get("selfconn", True),
+                              depthwise=kw.get("depthwise", False), DSweight=p.get("DSweight"))
+    np.testing.assert_array_equal(out.detach().numpy(), CV_Z[n + "/out"])      # same ops, same order: bit-equal
+    out.backward(torch.tensor(CV_Z[n + "/gout"]))
+    np.testing.assert_allclose(x.grad.numpy(), CV_Z[n + "/gx"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ea.grad.numpy(), CV_Z[n + "/gea"], rtol=1e-6, atol=1e-6)
+    for k, v in p.items():
+        np.testing.assert_allclose(v.grad.numpy(), CV_Z[n + "/g/" + k], rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", [c for c in CV_META if c["kind"] == "conv" and not c["kw"].get("depthwise")
+                                  and not c["kw"].get("selfconn", True)], ids=lambda c: c["name"])
+def test_dense_support_identity(case):
+    """sum_k S_k X W_k (libs/layers_tf.py:231-236) equals the edge-list form (libs/spect_conv.py:76-80)."""
+    n = case["name"]
+    p = _params(CV_Z, n)
+    out = O.spectconv_forward_dense(torch.tensor(CV_Z[n + "/x"]), torch.tensor(CV_Z[n + "/ei"]),
+                                    torch.tensor(CV_Z[n + "/ea"]), p["weight"], p.get("bias"))
+    ref = CV_Z[n + "/out"]
+    np.testing.assert_allclose(out.numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("case", [c for c in CV_META if c["kind"] == "layer"], ids=lambda c: c["name"])
+def test_ml3layer_matches_reference(case):
+    n = case["name"]
+    learnedge, kin, kout, ninp, nout1, nout2 = case["args"]
+    p = {k: v.requires_grad_(True) for k, v in _params(CV_Z, n).items()}
+    assert list(p.keys()) == case["keys"]
+    x = torch.tensor(CV_Z[n + "/x"], requires_grad=True)
+    ea = torch.tensor(CV_Z[n + "/ea"], requires_grad=True)
+    out = O.ml3layer_forward(x, torch.tensor(CV_Z[n + "/ei"]), ea, p, learnedge, nout2)
+    np.testing.assert_allclose(out.detach().numpy(), CV_Z[n + "/out"], rtol=1e-6, atol=1e-6)
+    out.backward(torch.tensor(CV_Z[n + "/gout"]))
+    np.testing.assert_allclose(x.grad.numpy(), CV_Z[n + "/gx"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(ea.grad.numpy(), CV_Z[n + "/gea"], rtol=1e-5, atol=1e-5)
+    for k, v in p.items():
+        np.testing.assert_allclose(v.grad.numpy(), CV_Z[n + "/g/" + k], rtol=1e-5, atol=1e-4)
+
+
+def test_oracle_module_keys_and_init():
+    m = O.OracleML3Layer(True, 6, 6, 2, 32, 16)
+    assert [k for k, _ in m.named_parameters()] == ["fc1_1.weight", "fc1_2.weight", "fc1_3.weight", "fc1_4.weight",
+                                                    "conv1.weight", "conv1.bias", "fc11.weight", "fc11.bias",
+                                                    "fc12.weight", "fc12.bias"]
+    s = (6.0 / (2 + 32)) ** 0.5
+    assert m.conv1.weight.abs().max() <= s and m.conv1.bias.abs().max() == 0
+
+
+def test_graph8c_model_fixture():
+    """graph8c.py:249-279 forward on the first 300 graphs with the reference's seed-0 weights."""
+    z, _ = load_npz("graph8c_model.npz")
+    g8 = O.parse_graph6(os.path.join(GOLDEN, "graph8c.g6"))
+    assert len(g8) == 11117 and all(n == 8 for n, _ in g8)
+    graphs = [O.spectral_design(ei, np.ones((n, 1), np.float32), recfield=1, dv=2, nfreq=5, adddegree=True)
+              for n, ei in g8[:300]]
+    model = O.OracleGNNML3("graph8c", ne=6, ninp=2)
+    model.load_state_dict({k[2:]: torch.tensor(z[k]) for k in z.files if k.startswith("p/")})
+    assert sum(p.numel() for p in model.parameters()) == 23714
+    with torch.no_grad():
+        emb = torch.cat([model(O.collate(graphs[i:i + 100])) for i in range(0, 300, 100)])
+    np.testing.assert_allclose(emb.numpy(), z["emb"], rtol=1e-5, atol=1e-6)
+
+
+def test_collate_and_pool_semantics():
+    g = [dict(x=np.ones((3, 2), np.float32), edge_index2=np.array([[0, 1, 2], [1, 2, 0]]), edge_attr2=np.ones((3, 4), np.float32), y=1.0),
+         dict(x=2 * np.ones((2, 2), np.float32), edge_index2=np.array([[0, 1], [1, 0]]), edge_attr2=np.zeros((2, 4), np.float32), y=0.0)]
+    b = O.collate(g)
+    assert b["edge_index2"].tolist() == [[0, 1, 2, 3, 4], [1, 2, 0, 4, 3]]
+    assert b["batch"].tolist() == [0, 0, 0, 1, 1] and b["y"].shape == (2, 1)
+    assert O.global_add_pool(b["x"], b["batch"], 2).tolist() == [[3, 3], [4, 4]]
+    assert O.global_mean_pool(b["x"], b["batch"], 2).tolist() == [[1, 1], [2, 2]]
+
+
+def test_spectral_design_invariants():
+    """identity column == [src == dst]; adjacency column == [src != dst] for recfield 1;
+    edge_index2 strictly increasing in src * n + dst."""
+    for c in SD_META:
+        n = c["name"]
+        ei2, ea2 = SD_Z[n + "/ei2"], SD_Z[n + "/ea2"]
+        nn = SD_Z[n + "/x"].shape[0]
+        nf = c["kw"]["nfreq"]
+        assert np.all(np.diff(ei2[0] * nn + ei2[1]) > 0)
+        assert np.array_equal(ea2[:, nf], (ei2[0] == ei2[1]).astype(np.float32))
+        if c["kw"].get("addadj") and c["kw"]["recfield"] == 1:
+            assert np.array_equal(ea2[:, nf + 1], (ei2[0] != ei2[1]).astype(np.float32))
