@@ -1,0 +1,54 @@
+// Shared helpers for the gnnml3_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/gnnml3_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "gnnml3_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace gnnml3 {
+
+// thread-local last-error string (the autograd engine calls backward from its own thread)
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+void count_launch(int n);
+
+#define GNNML3_REQUIRE(cond, ...)                                        \
+    do {                                                                 \
+        if (!(cond)) return ::gnnml3::set_err(GNNML3_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define GNNML3_CUDA(expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ::gnnml3::set_err(GNNML3_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, \
+                                     cudaGetErrorString(_e));                                      \
+    } while (0)
+
+#define GNNML3_LAUNCH_CHECK()           \
+    do {                              \
+        ::gnnml3::count_launch(1);    \
+        GNNML3_CUDA(cudaGetLastError()); \
+    } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+// streaming 128-bit store that does not pollute L1 (outputs are written once)
+__device__ __forceinline__ void st_na4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace gnnml3

@@ -1,0 +1,138 @@
+// Node-side epilogue of ML3Layer and the graph readout.
+//
+//   ml3_act_fwd : y = [ relu(c) || tanh(p1) * tanh(p2) ]   from pre = [c | p1 | p2]   (reference libs/spect_conv.py:209-212:
+//                 relu(conv1(...)), tanh(fc11 x) * tanh(fc12 x), torch.cat -- five elementwise launches + a cat there)
+//   ml3_act_bwd : gradient of the above w.r.t. pre (recomputes the tanh values; nothing extra is saved)
+//   segment_pool: global_add_pool / global_mean_pool (graph8c.py:277, Zinc12k.py:343, exp_classify.py:293,
+//                 counting.py:370) over the contiguous node range of every graph of the batch -- a segmented
+//                 sum in node order, no atomics.
+#include "common.cuh"
+
+namespace gnnml3 {
+
+__global__ void k_ml3_act_fwd(const float* __restrict__ pre, int64_t ldp, int64_t N, int Fo, int G, float* __restrict__ y,
+                              int64_t ldy) {
+    const int W = Fo + G;
+    const int64_t total = N * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / W;
+        const int c = (int)(i - n * W);
+        const float* p = pre + n * ldp;
+        float v;
+        if (c < Fo) {
+            v = fmaxf(__ldg(p + c), 0.f);
+        } else {
+            v = tanhf(__ldg(p + c)) * tanhf(__ldg(p + c + G));
+        }
+        y[n * ldy + c] = v;
+    }
+}
+
+// gpre[:, :Fo] = gy[:, :Fo] * (c > 0);  gpre[:, Fo+g] = gy[:, Fo+g] * t2 * (1 - t1^2);  gpre[:, Fo+G+g] = gy[:, Fo+g] * t1 * (1 - t2^2)
+// gate_out (optional) receives a second copy of the 2G gate-gradient columns (row stride ldgate).
+__global__ void k_ml3_act_bwd(const float* __restrict__ pre, int64_t ldp, const float* __restrict__ gy, int64_t ldy, int64_t N,
+                              int Fo, int G, float* __restrict__ gpre, int64_t ldg, float* __restrict__ gate_out,
+                              int64_t ldgate) {
+    const int W = Fo + G;
+    const int64_t total = N * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / W;
+        const int c = (int)(i - n * W);
+        const float* p = pre + n * ldp;
+        const float g = __ldg(gy + n * ldy + c);
+        if (c < Fo) {
+            gpre[n * ldg + c] = __ldg(p + c) > 0.f ? g : 0.f;
+        } else {
+            const float t1 = tanhf(__ldg(p + c)), t2 = tanhf(__ldg(p + c + G));
+            const float g1 = g * t2 * (1.f - t1 * t1), g2 = g * t1 * (1.f - t2 * t2);
+            gpre[n * ldg + c] = g1;
+            gpre[n * ldg + c + G] = g2;
+            if (gate_out) {
+                gate_out[n * ldgate + (c - Fo)] = g1;
+                gate_out[n * ldgate + (c - Fo) + G] = g2;
+            }
+        }
+    }
+}
+
+// one warp per (graph, 32-feature chunk)
+__global__ void __launch_bounds__(256) k_segment_pool_fwd(const float* __restrict__ x, int64_t ldx, const int* __restrict__ gptr,
+                                                          int B, int F, int mean, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int chunks = (F + 31) / 32;
+    const int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)B * chunks) return;
+    const int b = (int)(w / chunks), f = (int)(w % chunks) * 32 + lane;
+    const int n0 = __ldg(gptr + b), n1 = __ldg(gptr + b + 1);
+    if (f >= F) return;
+    float s = 0.f;
+    for (int n = n0; n < n1; ++n) s += __ldg(x + (int64_t)n * ldx + f);
+    if (mean) s /= (float)max(n1 - n0, 1);
+    out[(int64_t)b * F + f] = s;
+}
+
+__global__ void __launch_bounds__(256) k_segment_pool_bwd(const float* __restrict__ gout, const int* __restrict__ gptr, int B,
+                                                          int F, int mean, float* __restrict__ gx, int64_t ldx) {
+    const int lane = threadIdx.x & 31;
+    const int chunks = (F + 31) / 32;
+    const int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)B * chunks) return;
+    const int b = (int)(w / chunks), f = (int)(w % chunks) * 32 + lane;
+    const int n0 = __ldg(gptr + b), n1 = __ldg(gptr + b + 1);
+    if (f >= F) return;
+    float g = __ldg(gout + (int64_t)b * F + f);
+    if (mean) g /= (float)max(n1 - n0, 1);
+    for (int n = n0; n < n1; ++n) gx[(int64_t)n * ldx + f] = g;
+}
+
+static int ew_grid(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace gnnml3
+
+using namespace gnnml3;
+
+extern "C" int gnnml3_ml3_act_fwd(const float* pre, int64_t ldp, int64_t N, int Fo, int G, float* y, int64_t ldy, void* stream_) {
+    GNNML3_REQUIRE(N >= 0 && Fo >= 0 && G >= 0 && Fo + G > 0, "ml3_act_fwd: bad shape");
+    if (N == 0) return GNNML3_OK;
+    GNNML3_REQUIRE(pre && y && ldp >= Fo + 2 * G && ldy >= Fo + G, "ml3_act_fwd: bad arguments");
+    k_ml3_act_fwd<<<ew_grid(N * (Fo + G)), 256, 0, (cudaStream_t)stream_>>>(pre, ldp, N, Fo, G, y, ldy);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+extern "C" int gnnml3_ml3_act_bwd(const float* pre, int64_t ldp, const float* gy, int64_t ldy, int64_t N, int Fo, int G,
+                                  float* gpre, int64_t ldg, float* gate_out, int64_t ldgate, void* stream_) {
+    GNNML3_REQUIRE(N >= 0 && Fo >= 0 && G >= 0 && Fo + G > 0, "ml3_act_bwd: bad shape");
+    if (N == 0) return GNNML3_OK;
+    GNNML3_REQUIRE(pre && gy && gpre && ldp >= Fo + 2 * G && ldy >= Fo + G && ldg >= Fo + 2 * G, "ml3_act_bwd: bad arguments");
+    GNNML3_REQUIRE(gate_out == nullptr || ldgate >= 2 * G, "ml3_act_bwd: ldgate too small");
+    k_ml3_act_bwd<<<ew_grid(N * (Fo + G)), 256, 0, (cudaStream_t)stream_>>>(pre, ldp, gy, ldy, N, Fo, G, gpre, ldg, gate_out, ldgate);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+extern "C" int gnnml3_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int B, int F, int mean,
+                                       float* out, void* stream_) {
+    GNNML3_REQUIRE(B >= 0 && F > 0, "segment_pool_fwd: bad shape");
+    if (B == 0) return GNNML3_OK;
+    GNNML3_REQUIRE(x && graph_ptr && out && ldx >= F, "segment_pool_fwd: bad arguments");
+    const int64_t warps = (int64_t)B * ((F + 31) / 32);
+    k_segment_pool_fwd<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(x, ldx, graph_ptr, B, F, mean, out);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+extern "C" int gnnml3_segment_pool_bwd(const float* gout, const int32_t* graph_ptr, int B, int F, int mean, float* gx,
+                                       int64_t ldx, void* stream_) {
+    GNNML3_REQUIRE(B >= 0 && F > 0, "segment_pool_bwd: bad shape");
+    if (B == 0) return GNNML3_OK;
+    GNNML3_REQUIRE(gout && graph_ptr && gx && ldx >= F, "segment_pool_bwd: bad arguments");
+    const int64_t warps = (int64_t)B * ((F + 31) / 32);
+    k_segment_pool_bwd<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(gout, graph_ptr, B, F, mean, gx, ldx);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}

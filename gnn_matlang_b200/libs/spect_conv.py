@@ -1,0 +1,376 @@
+"""Drop-in replacements for the reference's ``libs/spect_conv.py`` modules (same import path suffix, same
+constructor / forward signatures, parameter names, shapes, initialisation and ``state_dict`` keys):
+
+    from gnn_matlang_b200.libs.spect_conv import SpectConv, ML3Layer
+
+* ``SpectConv(in_channels, out_channels, K=1, selfconn=True, depthwise=False, bias=True)``
+  -- reference libs/spect_conv.py:23-103 (a PyG ``MessagePassing`` module there).
+* ``ML3Layer(learnedge, nedgeinput, nedgeoutput, ninp, nout1, nout2)`` -- reference libs/spect_conv.py:182-212.
+
+What runs underneath is different: instead of K x (index_select, mul, scatter_add, matmul, add) the batch's
+edge list is turned once into a dst-sorted CSR (``graph.GraphPlan``), one segmented-reduction kernel applies
+all K edge-weight channels, and the per-support projections are ONE tensor-core contraction over K*F_in.
+The backward is atomic-free and deterministic:  with G_k = S_k^T grad_out (the same kernel over the
+transposed CSR)  dx = [G_0..G_{K-1}] W'^T,  dW_k = x^T G_k,  d edge_attr = SDDMM(x, grad_out W^T).
+All arithmetic happens in libgnnml3_b200.so; there is no CPU fallback (CPU tensors raise RuntimeError).
+"""
+import math
+
+import torch
+import torch.nn as nn
+from torch.nn import Parameter
+
+from .. import _lib, ops
+from ..graph import get_plan, sorted_edge_attr
+
+_PRECISIONS = {"fp32": _lib.PREC_3XTF32, "3xtf32": _lib.PREC_3XTF32, "tf32": _lib.PREC_TF32}
+
+
+def glorot(tensor):
+    """reference libs/spect_conv.py:13-16"""
+    if tensor is not None:
+        stdv = math.sqrt(6.0 / (tensor.size(-2) + tensor.size(-1)))
+        tensor.data.uniform_(-stdv, stdv)
+
+
+def zeros(tensor):
+    """reference libs/spect_conv.py:18-20"""
+    if tensor is not None:
+        tensor.data.fill_(0)
+
+
+def _aggregate(plan, ea_s, x, width_blocks, transposed=False):
+    """[N, width_blocks*F] buffer whose first K blocks are the K-channel aggregates of ``x``."""
+    N, F = x.shape
+    K = ea_s.size(1)
+    out = torch.empty(N, width_blocks * F, dtype=torch.float32, device=x.device)
+    if plan.E == 0:
+        out[:, :K * F].zero_()
+    elif transposed:
+        ops.spmm_k(plan.rowptrT, plan.colT, plan.permT, ea_s, x, out=out)
+    else:
+        ops.spmm_k(plan.rowptr, plan.col, None, ea_s, x, out=out)
+    return out
+
+
+class _SpectConvFn(torch.autograd.Function):
+    """out = sum_k P_k(x) W_k (+ x W_K if selfconn) (+ bias)   -- reference libs/spect_conv.py:70-80,93-94."""
+
+    @staticmethod
+    def forward(ctx, x, ea_s, weight, bias, plan, selfconn, precision):
+        x = x.contiguous()
+        ea_s = ea_s.contiguous()
+        weight = weight.contiguous()
+        N, Fi = x.shape
+        Kw, _, Fo = weight.shape
+        K = ea_s.size(1)
+        H = _aggregate(plan, ea_s, x, Kw)
+        if selfconn:
+            H[:, K * Fi:] = x
+        out = ops.gemm_nn(H, weight.view(Kw * Fi, Fo), bias, precision=precision)
+        ctx.save_for_backward(x, ea_s, weight)
+        ctx.plan, ctx.selfconn, ctx.precision, ctx.has_bias = plan, selfconn, precision, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, ea_s, weight = ctx.saved_tensors
+        plan, prec = ctx.plan, ctx.precision
+        gout = gout.contiguous()
+        N, Fi = x.shape
+        Kw, _, Fo = weight.shape
+        K = ea_s.size(1)
+        need_x, need_ea, need_w, need_b = ctx.needs_input_grad[:4]
+        dx = dea = dw = db = None
+        if N == 0:
+            return (torch.zeros_like(x) if need_x else None, torch.zeros_like(ea_s) if need_ea else None,
+                    torch.zeros_like(weight) if need_w else None,
+                    torch.zeros(Fo, device=x.device) if (need_b and ctx.has_bias) else None, None, None, None)
+        if need_x or need_w:
+            G = _aggregate(plan, ea_s, gout, Kw, transposed=True)           # G_k = S_k^T gout  [N, Kw*Fo]
+            if ctx.selfconn:
+                G[:, K * Fo:] = gout
+            if need_x:
+                dx = ops.gemm_nn(G, weight.transpose(1, 2).contiguous().view(Kw * Fo, Fi), precision=prec)
+            if need_w:
+                dw = ops.gemm_tn(x, G, precision=prec).view(Fi, Kw, Fo).permute(1, 0, 2).contiguous()
+        if need_b and ctx.has_bias:
+            db = ops.colsum(gout)
+        if need_ea:
+            if plan.E == 0:
+                dea = torch.zeros_like(ea_s)
+            else:
+                wp = weight[:K].permute(2, 0, 1).reshape(Fo, K * Fi).contiguous()
+                dH = ops.gemm_nn(gout, wp, precision=prec)                   # [N, K*Fi]
+                dea = ops.sddmm_k(plan.rowptr, plan.col, None, x, dH, K, plan.E)
+        return dx, dea, dw, db, None, None, None
+
+
+class _DepthwiseAggFn(torch.autograd.Function):
+    """Z = sum_k scale[k] * P_k(x)   -- the aggregation of the depthwise branch (reference :81-89)."""
+
+    @staticmethod
+    def forward(ctx, x, ea_s, scale, plan):
+        x, ea_s, scale = x.contiguous(), ea_s.contiguous(), scale.contiguous()
+        N, F = x.shape
+        K = ea_s.size(1)
+        H = _aggregate(plan, ea_s, x, K)
+        ctx.save_for_backward(x, ea_s, scale, H)
+        ctx.plan = plan
+        return (H.view(N, K, F) * scale.unsqueeze(0)).sum(1)
+
+    @staticmethod
+    def backward(ctx, dZ):
+        x, ea_s, scale, H = ctx.saved_tensors
+        plan = ctx.plan
+        dZ = dZ.contiguous()
+        N, F = x.shape
+        K = ea_s.size(1)
+        G = _aggregate(plan, ea_s, dZ, K, transposed=True)
+        dx = (G.view(N, K, F) * scale.unsqueeze(0)).sum(1)
+        dscale = (H.view(N, K, F) * dZ.unsqueeze(1)).sum(0)
+        if plan.E == 0:
+            dea = torch.zeros_like(ea_s)
+        else:
+            g = (dZ.unsqueeze(1) * scale.unsqueeze(0)).reshape(N, K * F).contiguous()
+            dea = ops.sddmm_k(plan.rowptr, plan.col, None, x, g, K, plan.E)
+        return dx, dea, dscale, None
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x @ Wt (+ b) with Wt [in, out]; tensor-core GEMMs of this library in both directions."""
+
+    @staticmethod
+    def forward(ctx, x, wt, bias, precision):
+        x, wt = x.contiguous(), wt.contiguous()
+        ctx.save_for_backward(x, wt)
+        ctx.precision, ctx.has_bias = precision, bias is not None
+        return ops.gemm_nn(x, wt, bias, precision=precision)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wt = ctx.saved_tensors
+        g = g.contiguous()
+        dx = dw = db = None
+        if x.size(0) == 0:
+            return torch.zeros_like(x), torch.zeros_like(wt), (torch.zeros(wt.size(1), device=x.device) if ctx.has_bias else None), None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm_nn(g, wt.t().contiguous(), precision=ctx.precision)
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm_tn(x, g, precision=ctx.precision)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(g)
+        return dx, dw, db, None
+
+
+class _ML3LayerFn(torch.autograd.Function):
+    """Whole ML3Layer (reference libs/spect_conv.py:204-212) as one autograd node:
+
+        ea' = edge_mlp(ea)                       (fused per-edge kernel; skipped if ``fused_edge`` is False)
+        pre = [ [P_0(x)..P_{K-1}(x)] Wc + b | x W11^T + b11 | x W12^T + b12 ]
+        y   = [ relu(pre_c) || tanh(pre_1) * tanh(pre_2) ]
+
+    Backward (atomic-free): d pre from the activation kernel; G' = [S_0^T gc .. S_{K-1}^T gc | gp1 | gp2];
+    dx = G' [Wc'^T ; W11 ; W12];  [dWc | dW11^T | dW12^T] = x^T G';  biases = column sums of d pre;
+    d ea' = SDDMM(x, gc Wc^T) and then through the edge MLP (activations recomputed)."""
+
+    @staticmethod
+    def forward(ctx, x, ea_s, w1, w2, w3, w4, wconv, bconv, w11, b11, w12, b12, plan, fused_edge, precision):
+        x, ea_s = x.contiguous(), ea_s.contiguous()
+        wconv = wconv.contiguous()
+        N, Fi = x.shape
+        K, _, Fo = wconv.shape
+        G = 0 if w11 is None else w11.size(0)
+        if fused_edge:
+            w1, w2, w3, w4 = w1.contiguous(), w2.contiguous(), w3.contiguous(), w4.contiguous()
+            ea2 = ops.edge_mlp_fwd(ea_s, None, w1, w2, w3, w4)
+        else:
+            ea2 = ea_s
+        H = _aggregate(plan, ea2, x, K)
+        pre = torch.empty(N, Fo + 2 * G, dtype=torch.float32, device=x.device)
+        if N > 0:
+            ops.gemm_nn(H, wconv.view(K * Fi, Fo), bconv, precision=precision, out=pre[:, :Fo])
+            if G > 0:
+                wg = torch.cat([w11.t(), w12.t()], 1).contiguous()
+                ops.gemm_nn(x, wg, torch.cat([b11, b12]), precision=precision, out=pre[:, Fo:])
+        y = ops.ml3_act_fwd(pre, Fo, G)
+        ctx.save_for_backward(x, ea_s, ea2 if fused_edge else None, pre, w1, w2, w3, w4, wconv, w11, w12)
+        ctx.plan, ctx.fused_edge, ctx.precision, ctx.G = plan, fused_edge, precision, G
+        ctx.has_bias = bconv is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, ea_s, ea2, pre, w1, w2, w3, w4, wconv, w11, w12 = ctx.saved_tensors
+        plan, prec, G = ctx.plan, ctx.precision, ctx.G
+        if ea2 is None:
+            ea2 = ea_s
+        N, Fi = x.shape
+        K, _, Fo = wconv.shape
+        need = ctx.needs_input_grad
+        gy = gy.contiguous()
+        Gp = torch.empty(N, K * Fo + 2 * G, dtype=torch.float32, device=x.device)
+        gpre = ops.ml3_act_bwd(pre, gy, Fo, G, gate_out=Gp[:, K * Fo:] if G > 0 else None)
+        gc = gpre[:, :Fo]
+        dx = dea = None
+        dws = [None, None, None, None]
+        dwc = dbc = dw11 = db11 = dw12 = db12 = None
+        if N == 0:
+            z = torch.zeros_like
+            return (z(x), z(ea_s), *(z(w) if w is not None else None for w in (w1, w2, w3, w4)), z(wconv),
+                    torch.zeros(Fo, device=x.device) if ctx.has_bias else None,
+                    z(w11) if G else None, torch.zeros(G, device=x.device) if G else None,
+                    z(w12) if G else None, torch.zeros(G, device=x.device) if G else None, None, None, None)
+        if plan.E == 0:
+            Gp[:, :K * Fo].zero_()
+        else:
+            ops.spmm_k(plan.rowptrT, plan.colT, plan.permT, ea2, gc, out=Gp)
+        if need[0]:
+            blocks = [wconv.transpose(1, 2).reshape(K * Fo, Fi)]
+            if G > 0:
+                blocks += [w11, w12]
+            dx = ops.gemm_nn(Gp, torch.cat(blocks, 0).contiguous(), precision=prec)
+        dcat = ops.gemm_tn(x, Gp, precision=prec)                                   # [Fi, K*Fo + 2G]
+        dwc = dcat[:, :K * Fo].reshape(Fi, K, Fo).permute(1, 0, 2).contiguous()
+        dball = ops.colsum(gpre)
+        if ctx.has_bias:
+            dbc = dball[:Fo].contiguous()
+        if G > 0:
+            dw11 = dcat[:, K * Fo:K * Fo + G].t().contiguous()
+            dw12 = dcat[:, K * Fo + G:].t().contiguous()
+            db11 = dball[Fo:Fo + G].contiguous()
+            db12 = dball[Fo + G:].contiguous()
+        if ctx.fused_edge or need[1]:
+            if plan.E == 0:
+                dea2 = torch.zeros_like(ea2)
+            else:
+                wp = wconv.permute(2, 0, 1).reshape(Fo, K * Fi).contiguous()
+                dH = ops.gemm_nn(gc, wp, precision=prec)
+                dea2 = ops.sddmm_k(plan.rowptr, plan.col, None, x, dH, K, plan.E)
+            if ctx.fused_edge:
+                dea, dws = ops.edge_mlp_bwd(ea_s, None, dea2, w1, w2, w3, w4, need_dea=need[1])
+            else:
+                dea = dea2
+        return (dx, dea, dws[0], dws[1], dws[2], dws[3], dwc, dbc, dw11, db11, dw12, db12, None, None, None)
+
+
+def _check_inputs(x, edge_index, edge_attr):
+    if not (x.is_cuda and edge_index.is_cuda and edge_attr.is_cuda):
+        raise RuntimeError("gnn_matlang_b200: x, edge_index and edge_attr must be CUDA tensors "
+                           "(the B200 hot path has no CPU fallback)")
+    if x.dim() != 2 or x.dtype != torch.float32 or edge_attr.dtype != torch.float32:
+        raise RuntimeError("gnn_matlang_b200: x [N,F] and edge_attr [E,K] must be float32")
+
+
+class SpectConv(nn.Module):
+    r"""Spectral convolution with K supports given as edge features (reference libs/spect_conv.py:23-103).
+
+    ``forward(x, edge_index, edge_attr)``: ``x [N, in]``, ``edge_index [2, E]`` int64 (row 0 source, row 1
+    target), ``edge_attr [E, K]``; returns ``[N, out]``.  ``edge_weight``, ``batch`` and ``lambda_max`` are
+    accepted and ignored exactly as in the reference (:64-65).
+    """
+
+    def __init__(self, in_channels, out_channels, K=1, selfconn=True, depthwise=False, bias=True, **kwargs):
+        kwargs.setdefault('aggr', 'add')
+        if kwargs.pop('aggr') != 'add':
+            raise ValueError("SpectConv only implements aggr='add' (the reference's default, :27)")
+        self.precision = kwargs.pop('precision', 'fp32')
+        if self.precision not in _PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+        super(SpectConv, self).__init__()
+        assert K > 0
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.depthwise = depthwise
+        self.selfconn = selfconn
+        if self.selfconn:
+            K = K + 1
+        if self.depthwise:
+            self.DSweight = Parameter(torch.Tensor(K, in_channels))
+            self.nsup = K
+            K = 1
+        self.weight = Parameter(torch.Tensor(K, in_channels, out_channels))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot(self.weight)
+        zeros(self.bias)
+        if self.depthwise:
+            zeros(self.DSweight)
+
+    def forward(self, x, edge_index, edge_attr, edge_weight=None, batch=None, lambda_max=None):
+        _check_inputs(x, edge_index, edge_attr)
+        plan = get_plan(edge_index, x.size(0))
+        return self.forward_sorted(x, plan, sorted_edge_attr(edge_attr, plan))
+
+    def forward_sorted(self, x, plan, ea_s):
+        """Same as ``forward`` with the graph plan and the dst-sorted edge features already at hand."""
+        prec = _PRECISIONS[self.precision]
+        if not self.depthwise:
+            nk = self.weight.size(0) - (1 if self.selfconn else 0)
+            if ea_s.size(1) < nk:
+                raise RuntimeError("SpectConv: edge_attr has %d channels but the layer was built with K=%d"
+                                   % (ea_s.size(1), nk))
+            if ea_s.size(1) > nk:          # the reference only reads edge_attr[:, i] for i < K (:76-77)
+                ea_s = ea_s[:, :nk]
+            return _SpectConvFn.apply(x, ea_s, self.weight, self.bias, plan, self.selfconn, prec)
+        nk = self.nsup - (1 if self.selfconn else 0)
+        if ea_s.size(1) < nk:
+            raise RuntimeError("SpectConv(depthwise): edge_attr has %d channels, need %d" % (ea_s.size(1), nk))
+        scale = self.DSweight[:nk] + torch.cat([torch.ones(1, self.in_channels, device=x.device),
+                                                torch.zeros(nk - 1, self.in_channels, device=x.device)], 0)
+        z = _DepthwiseAggFn.apply(x, ea_s[:, :nk], scale, plan)
+        if self.selfconn:
+            z = z + x * self.DSweight[-1]
+        return _LinearFn.apply(z, self.weight[0], self.bias, prec)
+
+    def __repr__(self):
+        return '{}({}, {}, K={})'.format(self.__class__.__name__, self.in_channels, self.out_channels,
+                                         self.weight.size(0))
+
+
+class ML3Layer(torch.nn.Module):
+    """GNNML3 layer (reference libs/spect_conv.py:182-212): learned edge features, SpectConv, tanh*tanh
+    gating branch, concatenation."""
+
+    def __init__(self, learnedge, nedgeinput, nedgeoutput, ninp, nout1, nout2, precision='fp32'):
+        super(ML3Layer, self).__init__()
+        self.learnedge = learnedge
+        self.nout2 = nout2
+        self.precision = precision
+        if self.learnedge:
+            self.fc1_1 = torch.nn.Linear(nedgeinput, 2 * nedgeinput, bias=False)
+            self.fc1_2 = torch.nn.Linear(nedgeinput, 2 * nedgeinput, bias=False)
+            self.fc1_3 = torch.nn.Linear(nedgeinput, 2 * nedgeinput, bias=False)
+            self.fc1_4 = torch.nn.Linear(4 * nedgeinput, nedgeoutput, bias=False)
+        else:
+            nedgeoutput = nedgeinput
+        self.conv1 = SpectConv(ninp, nout1, nedgeoutput, selfconn=False, precision=precision)
+        if nout2 > 0:
+            self.fc11 = torch.nn.Linear(ninp, nout2)
+            self.fc12 = torch.nn.Linear(ninp, nout2)
+
+    def forward(self, x, edge_index, edge_attr):
+        _check_inputs(x, edge_index, edge_attr)
+        plan = get_plan(edge_index, x.size(0))
+        ea = sorted_edge_attr(edge_attr, plan)
+        prec = _PRECISIONS[self.precision]
+        c = self.conv1
+        if ea.size(1) != (self.fc1_1.in_features if self.learnedge else c.weight.size(0)):
+            raise RuntimeError("ML3Layer: edge_attr has %d channels, expected %d"
+                               % (ea.size(1), self.fc1_1.in_features if self.learnedge else c.weight.size(0)))
+        fused_edge = self.learnedge and ops.edge_mlp_supported(self.fc1_1.in_features, self.fc1_4.out_features)
+        if self.learnedge and not fused_edge:
+            # shapes outside the fused per-edge kernel (odd K, K > 16, nedgeoutput != nedgeinput): the same MLP
+            # composed from this library's tensor-core GEMMs
+            tmp = torch.cat([torch.relu(_LinearFn.apply(ea, self.fc1_1.weight.t(), None, prec)),
+                             torch.tanh(_LinearFn.apply(ea, self.fc1_2.weight.t(), None, prec)) *
+                             torch.tanh(_LinearFn.apply(ea, self.fc1_3.weight.t(), None, prec))], 1)
+            ea = torch.relu(_LinearFn.apply(tmp, self.fc1_4.weight.t(), None, prec))
+        w = (self.fc1_1.weight, self.fc1_2.weight, self.fc1_3.weight, self.fc1_4.weight) if fused_edge else (None,) * 4
+        g = (self.fc11.weight, self.fc11.bias, self.fc12.weight, self.fc12.bias) if self.nout2 > 0 else (None,) * 4
+        return _ML3LayerFn.apply(x, ea, *w, c.weight, c.bias, *g, plan, fused_edge, prec)

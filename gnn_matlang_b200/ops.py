@@ -1,0 +1,262 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/gnnml3_b200.h).
+
+PyTorch is used here only for device memory (torch.empty on the input's device) and for the current
+stream; all arithmetic happens inside libgnnml3_b200.so.  Every wrapper refuses CPU tensors.
+"""
+import torch
+
+from . import _lib
+
+_workspaces = {}
+
+
+def _ws(device, nbytes, tag="main"):
+    """Grow-only per-device scratch buffer (stream-ordered reuse on the current stream)."""
+    key = (device.index, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32 (got %s)" % (name, t.dtype))
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: gnn_matlang_b200 has no CPU fallback" % name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows(t, name):
+    """float32 CUDA matrix whose rows are unit-stride (row stride may exceed the width: column-block views)."""
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32 (got %s)" % (name, t.dtype))
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: gnn_matlang_b200 has no CPU fallback" % name)
+    if t.dim() == 2 and (t.size(1) == 1 or t.stride(1) == 1) and (t.size(0) <= 1 or t.stride(0) >= t.size(1)):
+        return t
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ld(t):
+    """Row stride in floats (size-1 leading dims can carry arbitrary strides, so fall back to the width)."""
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
+
+
+def csr_build(edge_index, num_nodes, check_range=True):
+    """edge_index [2,E] int64 (row 0 = source, row 1 = target) -> dict of int32 CSR / transposed-CSR arrays."""
+    lib = _lib.load()
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
+    if not edge_index.is_cuda:
+        raise RuntimeError("edge_index must be a CUDA tensor: gnn_matlang_b200 has no CPU fallback")
+    ei = edge_index.contiguous()
+    E, N = ei.size(1), int(num_nodes)
+    dev = ei.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    out = dict(rowptr=torch.empty(N + 1, **i32), col=torch.empty(E, **i32), perm=torch.empty(E, **i32),
+               rowptrT=torch.empty(N + 1, **i32), colT=torch.empty(E, **i32), permT=torch.empty(E, **i32))
+    flag = torch.zeros(1, **i32)
+    nbytes = lib.gnnml3_csr_workspace_bytes(E, N)
+    ws = _ws(dev, nbytes)
+    with torch.cuda.device(dev):
+        rc = lib.gnnml3_csr_build(_lib.ptr(ei), E, N, _lib.ptr(out["rowptr"]), _lib.ptr(out["col"]), _lib.ptr(out["perm"]),
+                                  _lib.ptr(out["rowptrT"]), _lib.ptr(out["colT"]), _lib.ptr(out["permT"]),
+                                  _lib.ptr(flag), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "gnnml3_csr_build")
+    if check_range and int(flag.item()) != 0:
+        raise RuntimeError("edge_index contains node ids outside [0, %d)" % N)
+    return out
+
+
+def gather_rows(src, perm):
+    lib = _lib.load()
+    src = _f32c(src, "src")
+    rows, width = perm.numel(), src.size(1)
+    out = torch.empty(rows, width, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(lib.gnnml3_gather_rows(_lib.ptr(src), _lib.ptr(perm), rows, width, _lib.ptr(out), _lib.stream_ptr()),
+                   "gnnml3_gather_rows")
+    return out
+
+
+def scatter_rows(src, perm):
+    lib = _lib.load()
+    src = _f32c(src, "src")
+    rows, width = perm.numel(), src.size(1)
+    out = torch.empty(rows, width, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(lib.gnnml3_scatter_rows(_lib.ptr(src), _lib.ptr(perm), rows, width, _lib.ptr(out), _lib.stream_ptr()),
+                   "gnnml3_scatter_rows")
+    return out
+
+
+def spmm_k(rowptr, col, eperm, ea, x, out=None):
+    """out[t, k*F + f] = sum_{p in row t} ea[e(p), k] * x[col[p], f]  -> [N, K*F]"""
+    lib = _lib.load()
+    x = _rows(x, "x")
+    ea = _f32c(ea, "edge_attr")
+    N, F = x.shape
+    K = ea.size(1)
+    if out is None:
+        out = torch.empty(N, K * F, dtype=torch.float32, device=x.device)
+    if N == 0:
+        return out
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gnnml3_spmm_k(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(ea), _lib.ptr(x), _ld(x),
+                                     N, K, F, _lib.ptr(out), _ld(out), _lib.stream_ptr()), "gnnml3_spmm_k")
+    return out
+
+
+def sddmm_k(rowptr, col, eperm, x, g, K, E):
+    """dea[e(p), k] = <x[col[p]], g[t, k*F:(k+1)*F]>  -> [E, K]"""
+    lib = _lib.load()
+    x = _rows(x, "x")
+    g = _rows(g, "g")
+    N, F = x.shape
+    dea = torch.empty(E, K, dtype=torch.float32, device=x.device)
+    if N == 0 or E == 0:
+        return dea
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gnnml3_sddmm_k(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(x), _ld(x), _lib.ptr(g),
+                                      _ld(g), N, K, F, _lib.ptr(dea), _lib.stream_ptr()), "gnnml3_sddmm_k")
+    return dea
+
+
+def gemm_nn(A, B, bias=None, precision=_lib.PREC_3XTF32, epilogue=_lib.EPI_NONE, out=None):
+    """C = A @ B (+ bias) (+ relu) on the tensor cores; A [M,Kc], B [Kc,Nc]."""
+    lib = _lib.load()
+    A = _rows(A, "A")
+    B = _f32c(B, "B")
+    M, Kc = A.shape
+    Nc = B.size(1)
+    if B.size(0) != Kc:
+        raise RuntimeError("gemm_nn: inner dimensions differ (%d vs %d)" % (Kc, B.size(0)))
+    if out is None:
+        out = torch.empty(M, Nc, dtype=torch.float32, device=A.device)
+    if M == 0:
+        return out
+    if bias is not None:
+        bias = _f32c(bias, "bias")
+    with torch.cuda.device(A.device):
+        _lib.check(lib.gnnml3_gemm_nn(_lib.ptr(A), _ld(A), _lib.ptr(B), _ld(B), _lib.ptr(bias), _lib.ptr(out),
+                                      _ld(out), M, Nc, Kc, precision, epilogue, _lib.stream_ptr()), "gnnml3_gemm_nn")
+    return out
+
+
+def gemm_tn(A, B, precision=_lib.PREC_3XTF32):
+    """C = A^T @ B; A [M,Ka], B [M,Nb] -> [Ka,Nb]; deterministic split over M."""
+    lib = _lib.load()
+    A = _rows(A, "A")
+    B = _rows(B, "B")
+    M, Ka = A.shape
+    Nb = B.size(1)
+    out = torch.empty(Ka, Nb, dtype=torch.float32, device=A.device)
+    if M == 0:
+        return out.zero_()
+    nbytes = lib.gnnml3_gemm_tn_workspace_bytes(M, Ka, Nb)
+    ws = _ws(A.device, nbytes)
+    with torch.cuda.device(A.device):
+        _lib.check(lib.gnnml3_gemm_tn(_lib.ptr(A), _ld(A), _lib.ptr(B), _ld(B), _lib.ptr(out), _ld(out), M, Ka,
+                                      Nb, precision, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_gemm_tn")
+    return out
+
+
+def colsum(A):
+    lib = _lib.load()
+    A = _rows(A, "A")
+    M, Nc = A.shape
+    out = torch.empty(Nc, dtype=torch.float32, device=A.device)
+    if M == 0:
+        return out.zero_()
+    nbytes = lib.gnnml3_colsum_workspace_bytes(M, Nc)
+    ws = _ws(A.device, nbytes)
+    with torch.cuda.device(A.device):
+        _lib.check(lib.gnnml3_colsum(_lib.ptr(A), _ld(A), M, Nc, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                     _lib.stream_ptr()), "gnnml3_colsum")
+    return out
+
+
+def edge_mlp_supported(K, Kout):
+    return bool(_lib.load().gnnml3_edge_mlp_supported(int(K), int(Kout)))
+
+
+def edge_mlp_fwd(ea, eperm, w1, w2, w3, w4):
+    """relu(W4 [relu(W1 a) || tanh(W2 a) tanh(W3 a)]) per edge; output in the order of eperm (or ea's)."""
+    lib = _lib.load()
+    ea = _f32c(ea, "edge_attr")
+    w1, w2, w3, w4 = (_f32c(w, "w") for w in (w1, w2, w3, w4))
+    E, K = ea.shape
+    Kout = w4.size(0)
+    out = torch.empty(E, Kout, dtype=torch.float32, device=ea.device)
+    with torch.cuda.device(ea.device):
+        _lib.check(lib.gnnml3_edge_mlp_fwd(_lib.ptr(ea), _lib.ptr(eperm), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3), _lib.ptr(w4),
+                                           E, K, Kout, _lib.ptr(out), _lib.stream_ptr()), "gnnml3_edge_mlp_fwd")
+    return out
+
+
+def edge_mlp_bwd(ea, eperm, gout, w1, w2, w3, w4, need_dea):
+    lib = _lib.load()
+    ea = _f32c(ea, "edge_attr")
+    gout = _f32c(gout, "gout")
+    w1, w2, w3, w4 = (_f32c(w, "w") for w in (w1, w2, w3, w4))
+    E, K = ea.shape
+    Kout = w4.size(0)
+    dev = ea.device
+    dea = torch.empty_like(ea) if need_dea else None
+    dw = [torch.empty_like(w) for w in (w1, w2, w3, w4)]
+    nbytes = lib.gnnml3_edge_mlp_bwd_workspace_bytes(E, K)
+    ws = _ws(dev, nbytes)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gnnml3_edge_mlp_bwd(_lib.ptr(ea), _lib.ptr(eperm), _lib.ptr(gout), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3),
+                                           _lib.ptr(w4), E, K, Kout, _lib.ptr(dea), _lib.ptr(dw[0]), _lib.ptr(dw[1]),
+                                           _lib.ptr(dw[2]), _lib.ptr(dw[3]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "gnnml3_edge_mlp_bwd")
+    return dea, dw
+
+
+def ml3_act_fwd(pre, Fo, G):
+    lib = _lib.load()
+    N = pre.size(0)
+    y = torch.empty(N, Fo + G, dtype=torch.float32, device=pre.device)
+    with torch.cuda.device(pre.device):
+        _lib.check(lib.gnnml3_ml3_act_fwd(_lib.ptr(pre), _ld(pre), N, Fo, G, _lib.ptr(y), _ld(y), _lib.stream_ptr()),
+                   "gnnml3_ml3_act_fwd")
+    return y
+
+
+def ml3_act_bwd(pre, gy, Fo, G, gate_out=None):
+    """d pre [N, Fo+2G]; ``gate_out`` (a [N, >=2G] strided view) receives a copy of the gate columns."""
+    lib = _lib.load()
+    gy = _f32c(gy, "gy")
+    N = pre.size(0)
+    gpre = torch.empty(N, Fo + 2 * G, dtype=torch.float32, device=pre.device)
+    with torch.cuda.device(pre.device):
+        _lib.check(lib.gnnml3_ml3_act_bwd(_lib.ptr(pre), _ld(pre), _lib.ptr(gy), _ld(gy), N, Fo, G, _lib.ptr(gpre),
+                                          _ld(gpre), _lib.ptr(gate_out) if gate_out is not None else None,
+                                          _ld(gate_out) if gate_out is not None else 0, _lib.stream_ptr()),
+                   "gnnml3_ml3_act_bwd")
+    return gpre
+
+
+def segment_pool_fwd(x, graph_ptr, mean):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    B, F = graph_ptr.numel() - 1, x.size(1)
+    out = torch.empty(B, F, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gnnml3_segment_pool_fwd(_lib.ptr(x), _ld(x), _lib.ptr(graph_ptr), B, F, int(mean), _lib.ptr(out),
+                                               _lib.stream_ptr()), "gnnml3_segment_pool_fwd")
+    return out
+
+
+def segment_pool_bwd(gout, graph_ptr, mean, N):
+    lib = _lib.load()
+    gout = _f32c(gout, "gout")
+    B, F = gout.shape
+    gx = torch.empty(N, F, dtype=torch.float32, device=gout.device)
+    with torch.cuda.device(gout.device):
+        _lib.check(lib.gnnml3_segment_pool_bwd(_lib.ptr(gout), _lib.ptr(graph_ptr), B, F, int(mean), _lib.ptr(gx), _ld(gx),
+                                               _lib.stream_ptr()), "gnnml3_segment_pool_bwd")
+    return gx

@@ -1,0 +1,141 @@
+/*
+ * gnnml3_b200.h -- C ABI of the B200-native GNNML3 hot path (libgnnml3_b200.so, sm_100a only).
+ *
+ * Drop-in boundary for the hot path of balcilar/gnn-matlang (citations relative to the reference root):
+ *   libs/spect_conv.py:64-99   SpectConv.forward / message   (+ PyG MessagePassing.propagate, aggr='add')
+ *   libs/spect_conv.py:204-212 ML3Layer.forward              (edge MLP, tanh*tanh gating, concat)
+ *   libs/utils.py:546-610      SpectralDesign.__call__       (supports M .* U f_k(L) U^T as edge features)
+ *   PyG global_add_pool / global_mean_pool (graph8c.py:277, Zinc12k.py:343, exp_classify.py:293, counting.py:370)
+ *   PyG Batch.from_data_list collation of edge_index2 (Zinc12k.py:20-22 etc.)
+ * The reference is pure Python and has no FFI; the binding a maintainer would add is the ctypes stub shown
+ * in INTEGRATION.md (and implemented in gnn_matlang_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  Unless a parameter name ends in `_host`, every
+ *     pointer is a DEVICE pointer valid on the current CUDA device.
+ *   - all matrices are row-major FP32, indices are int32 inside the library; the reference's int64
+ *     edge_index [2,E] (row 0 = source j, row 1 = target i) is accepted by gnnml3_csr_build.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Nothing synchronises the
+ *     device except the *_host entry points and functions documented to do so; everything else is
+ *     CUDA-graph capturable.
+ *   - return value: 0 = success, otherwise one of GNNML3_ERR_*; gnnml3_last_error() returns a
+ *     thread-local human-readable message.  There is no CPU fallback anywhere in this library.
+ *   - determinism: no floating-point atomics; every reduction has a fixed order.
+ */
+#ifndef GNNML3_B200_H_
+#define GNNML3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GNNML3_API __attribute__((visibility("default")))
+#else
+#define GNNML3_API
+#endif
+
+#define GNNML3_OK 0
+#define GNNML3_ERR_INVALID 1     /* bad argument (shape, alignment, NULL, unsupported size) */
+#define GNNML3_ERR_CUDA 2        /* a CUDA runtime call or kernel launch failed */
+#define GNNML3_ERR_WORKSPACE 3   /* workspace too small */
+
+/* GEMM arithmetic: FP32-grade error-compensated 3xTF32 (default, meets rtol 1e-5), single-pass TF32. */
+#define GNNML3_PREC_3XTF32 0
+#define GNNML3_PREC_TF32 1
+
+/* epilogues of gnnml3_gemm_nn */
+#define GNNML3_EPI_NONE 0
+#define GNNML3_EPI_RELU 1
+
+GNNML3_API const char* gnnml3_last_error(void);
+GNNML3_API int gnnml3_version(void);
+/* number of kernels launched by this library in the calling process so far (for bench.py's gpu_launches) */
+GNNML3_API int64_t gnnml3_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Graph structure: dst-sorted CSR + src-sorted (transposed) CSR of the batched disjoint graph.
+ * Replaces the index_select / scatter_add indexing of PyG propagate (libs/spect_conv.py:77) and is
+ * bit-exact integer work: within a row, entries keep the original edge order (stable).
+ *   rowptr [N+1], col [E] (= source of the p-th dst-sorted edge), perm [E] (= original edge id of p)
+ *   rowptrT [N+1], colT [E] (= target of the q-th src-sorted edge), permT [E] (= dst-sorted position p of q)
+ * err_flag (device int32, may be NULL) is set to 1 if any index is outside [0, N).
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API size_t gnnml3_csr_workspace_bytes(int64_t E, int64_t N);
+GNNML3_API int gnnml3_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
+                     int32_t* rowptr, int32_t* col, int32_t* perm,
+                     int32_t* rowptrT, int32_t* colT, int32_t* permT,
+                     int32_t* err_flag, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[p, :] = in[perm[p], :]  (gather) and out[perm[p], :] = in[p, :] (scatter); rows of `width` floats */
+GNNML3_API int gnnml3_gather_rows(const float* in, const int32_t* perm, int64_t rows, int width, float* out, void* stream);
+GNNML3_API int gnnml3_scatter_rows(const float* in, const int32_t* perm, int64_t rows, int width, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K-channel segmented reduction (the aggregate of SpectConv, libs/spect_conv.py:76-77,98-99):
+ *   out[t, k*F + f] = sum_{p in [rowptr[t], rowptr[t+1])} ea[e(p), k] * x[col[p], f],  e(p) = eperm ? eperm[p] : p
+ * x [N, F] (ldx floats per row), ea [E, K] row-major, out [N, ldo] with ldo >= K*F.  Atomic-free, summation
+ * in row order.  Used forward with the dst-sorted CSR and backward (on grad_out) with the transposed CSR.
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_spmm_k(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea,
+                  const float* x, int64_t ldx, int64_t N, int K, int F, float* out, int64_t ldo, void* stream);
+
+/* d ea[e(p), k] = < x[col[p], :], g[t, k*F : (k+1)*F] >  for every edge p of every row t (SDDMM). */
+GNNML3_API int gnnml3_sddmm_k(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* x, int64_t ldx,
+                   const float* g, int64_t ldg, int64_t N, int K, int F, float* dea, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Tensor-core contractions (mma TF32 with FP32 accumulate; 3xTF32 split for FP32-grade results).
+ *   gemm_nn: C[M, Nc] = A[M, Kc] * B[Kc, Nc] (+ bias[Nc]) (+ epilogue)     -- projection  H * W
+ *   gemm_tn: C[Ka, Nb] = A[M, Ka]^T * B[M, Nb]                              -- weight gradient, fixed-order split-M
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
+                   float* C, int64_t ldc, int64_t M, int Nc, int Kc, int precision, int epilogue, void* stream);
+GNNML3_API size_t gnnml3_gemm_tn_workspace_bytes(int64_t M, int Ka, int Nb);
+GNNML3_API int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t M, int Ka, int Nb, int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* out[c] = sum_r A[r, c]  (bias gradient), fixed order */
+GNNML3_API size_t gnnml3_colsum_workspace_bytes(int64_t M, int Nc);
+GNNML3_API int gnnml3_colsum(const float* A, int64_t lda, int64_t M, int Nc, float* out, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused per-edge MLP of ML3Layer (libs/spect_conv.py:191-194,206-207):
+ *   out[p, :] = relu(W4 [relu(W1 a) || tanh(W2 a) * tanh(W3 a)]),  a = ea[e(p), :],  e(p) = eperm ? eperm[p] : p
+ * W1,W2,W3 [2K, K], W4 [Kout, 4K] are the nn.Linear.weight tensors (bias-free).  Instantiated for even
+ * K <= 16 with Kout == K (gnnml3_edge_mlp_supported); other shapes are composed from gnnml3_gemm_*.
+ * bwd recomputes the activations; dea (nullable) receives d ea at e(p); dw1..dw4 are overwritten.
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_edge_mlp_supported(int K, int Kout);
+GNNML3_API int gnnml3_edge_mlp_fwd(const float* ea, const int32_t* eperm, const float* w1, const float* w2, const float* w3,
+                        const float* w4, int64_t E, int K, int Kout, float* out, void* stream);
+GNNML3_API size_t gnnml3_edge_mlp_bwd_workspace_bytes(int64_t E, int K);
+GNNML3_API int gnnml3_edge_mlp_bwd(const float* ea, const int32_t* eperm, const float* gout, const float* w1, const float* w2,
+                        const float* w3, const float* w4, int64_t E, int K, int Kout, float* dea, float* dw1,
+                        float* dw2, float* dw3, float* dw4, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Node-side epilogue of ML3Layer (libs/spect_conv.py:209-212) on pre = [c | p1 | p2]  ([N, Fo + 2G]):
+ *   y = [relu(c) || tanh(p1) * tanh(p2)]  ([N, Fo + G]);  bwd gives d pre (and optionally a second copy of its
+ *   2G gate columns into gate_out, row stride ldgate).
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_ml3_act_fwd(const float* pre, int64_t ldp, int64_t N, int Fo, int G, float* y, int64_t ldy, void* stream);
+GNNML3_API int gnnml3_ml3_act_bwd(const float* pre, int64_t ldp, const float* gy, int64_t ldy, int64_t N, int Fo, int G,
+                       float* gpre, int64_t ldg, float* gate_out, int64_t ldgate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Readout: PyG global_add_pool (mean = 0) / global_mean_pool (mean = 1) over contiguous node ranges
+ * graph_ptr [B+1] (graph b owns nodes graph_ptr[b] .. graph_ptr[b+1]-1, as produced by batching).
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_segment_pool_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int B, int F, int mean,
+                            float* out, void* stream);
+GNNML3_API int gnnml3_segment_pool_bwd(const float* gout, const int32_t* graph_ptr, int B, int F, int mean, float* gx,
+                            int64_t ldx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNML3_B200_H_ */

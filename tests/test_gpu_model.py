@@ -1,0 +1,139 @@
+"""GPU parity of the fused layer pieces (edge MLP, activation, readout) and of whole GNNML3 models against
+the oracle and the reference-generated graph8c fixture.  FP32 bar as in test_gpu_kernels.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN, load_npz  # noqa: E402
+from oracle import gnnml3_oracle as O  # noqa: E402
+from test_gpu_kernels import assert_close, dev  # noqa: E402
+
+
+@pytest.mark.parametrize("K", [2, 4, 6, 8, 10, 12, 14, 16])
+@pytest.mark.parametrize("E", [1, 255, 1000, 70000])
+def test_edge_mlp_kernels(K, E):
+    from gnn_matlang_b200 import ops
+    g = torch.Generator().manual_seed(K * 100 + E)
+    ea = torch.randn(E, K, generator=g)
+    ws = [torch.randn(2 * K, K, generator=g) * 0.5 for _ in range(3)] + [torch.randn(K, 4 * K, generator=g) * 0.3]
+    perm = torch.randperm(E, generator=g)
+    gout = torch.randn(E, K, generator=g)
+    ea_r = ea.clone().requires_grad_(True)
+    ws_r = [w.clone().requires_grad_(True) for w in ws]
+    ref = O.edge_mlp_forward(ea_r[perm], *ws_r)
+    ref.backward(gout)
+    d = dev()
+    out = ops.edge_mlp_fwd(ea.to(d), perm.to(torch.int32).to(d), *[w.to(d) for w in ws])
+    assert_close(out, ref, name="edge mlp fwd")
+    dea, dws = ops.edge_mlp_bwd(ea.to(d), perm.to(torch.int32).to(d), gout.to(d), *[w.to(d) for w in ws], need_dea=True)
+    assert_close(dea, ea_r.grad, name="edge mlp d ea")
+    for i in range(4):
+        assert_close(dws[i], ws_r[i].grad, rtol=2e-5, name="edge mlp dW%d" % (i + 1))
+    # without d ea and without permutation; must be deterministic
+    _, dws2 = ops.edge_mlp_bwd(ea[perm].contiguous().to(d), None, gout.to(d), *[w.to(d) for w in ws], need_dea=False)
+    _, dws3 = ops.edge_mlp_bwd(ea[perm].contiguous().to(d), None, gout.to(d), *[w.to(d) for w in ws], need_dea=False)
+    for i in range(4):
+        assert_close(dws2[i], ws_r[i].grad, rtol=2e-5, name="edge mlp dW%d (sorted)" % (i + 1))
+        assert torch.equal(dws2[i], dws3[i])
+
+
+@pytest.mark.parametrize("mean", [False, True])
+def test_segment_pool(mean):
+    from gnn_matlang_b200.pool import global_add_pool, global_mean_pool
+    g = torch.Generator().manual_seed(3)
+    sizes = torch.randint(1, 40, (300,), generator=g)
+    batch = torch.repeat_interleave(torch.arange(300), sizes)
+    x = torch.randn(batch.numel(), 48, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = (O.global_mean_pool if mean else O.global_add_pool)(xr, batch, 300)
+    gout = torch.randn(300, 48, generator=g)
+    ref.backward(gout)
+    xg = x.to(dev()).requires_grad_(True)
+    out = (global_mean_pool if mean else global_add_pool)(xg, batch.to(dev()))
+    out.backward(gout.to(dev()))
+    assert_close(out, ref, name="pool")
+    assert_close(xg.grad, xr.grad, name="pool grad")
+    with pytest.raises(RuntimeError):
+        global_add_pool(xg, batch.flip(0).to(dev()))
+
+
+def test_graph8c_model_golden():
+    """graph8c.py:249-279 on the first 300 graphs with the reference's seed-0 weights (fixture made by the
+    unmodified reference) -- embeddings within the FP32 bar, and the batching is bit-exact."""
+    from gnn_matlang_b200.batch import collate
+    from gnn_matlang_b200.models import GNNML3
+    z, _ = load_npz("graph8c_model.npz")
+    g8 = O.parse_graph6(os.path.join(GOLDEN, "graph8c.g6"))
+    graphs = [O.spectral_design(ei, np.ones((n, 1), np.float32), recfield=1, dv=2, nfreq=5, adddegree=True) for n, ei in g8[:300]]
+    model = GNNML3("graph8c", ne=6, ninp=2)
+    model.load_state_dict({k[2:]: torch.tensor(z[k]) for k in z.files if k.startswith("p/")})
+    model = model.to(dev()).eval()
+    embs = []
+    with torch.no_grad():
+        for i in range(0, 300, 100):
+            hb = collate(graphs[i:i + 100])
+            ob = O.collate(graphs[i:i + 100])
+            assert torch.equal(hb.edge_index2, ob["edge_index2"]) and torch.equal(hb.batch, ob["batch"])
+            assert torch.equal(hb.x, ob["x"]) and torch.equal(hb.edge_attr2, ob["edge_attr2"])
+            embs.append(model(hb.to(dev())))
+    assert_close(torch.cat(embs), z["emb"], name="graph8c embeddings")
+
+
+def _random_graphs(cfg, nb, g):
+    """Small ZINC-/counting-/EXP-shaped graph records with real SpectralDesign supports from the oracle."""
+    rng = np.random.default_rng(int(torch.randint(0, 1 << 30, (1,), generator=g)))
+    kw = dict(zinc=dict(recfield=2, dv=2, nfreq=7), counting=dict(recfield=1, dv=1, nfreq=10, adddegree=True, laplacien=False, addadj=True),
+              exp=dict(recfield=1, dv=2, nfreq=5, adddegree=True), graph8c=dict(recfield=1, dv=2, nfreq=5, adddegree=True))[cfg]
+    out = []
+    for _ in range(nb):
+        n = int(rng.integers(9, 38))
+        up = np.triu(rng.random((n, n)) < 2.2 / n, 1)
+        up[np.arange(n - 1), np.arange(1, n)] = True
+        r, c = np.where(up | up.T)
+        x = np.zeros((n, 25), np.float32) if cfg == "zinc" else np.ones((n, 1), np.float32)
+        if cfg == "zinc":
+            x[np.arange(n), rng.integers(0, 25, n)] = 1
+        with np.errstate(all="ignore"):
+            d = O.spectral_design(np.vstack((r, c)), x, **kw)
+        d["y"] = np.float32(rng.standard_normal())
+        out.append(d)
+    return out
+
+
+@pytest.mark.parametrize("cfg", ["zinc", "counting", "exp", "graph8c"])
+def test_model_training_step_matches_oracle(cfg):
+    """forward, loss, every parameter gradient and one Adam step vs the oracle model with identical weights."""
+    from gnn_matlang_b200.batch import collate
+    from gnn_matlang_b200.models import GNNML3
+    g = torch.Generator().manual_seed(11)
+    graphs = _random_graphs(cfg, 24, g)
+    ne, ninp = graphs[0]["edge_attr2"].shape[1], graphs[0]["x"].shape[1]
+    torch.manual_seed(5)
+    ref = O.OracleGNNML3(cfg, ne, ninp)
+    model = GNNML3(cfg, ne, ninp)
+    model.load_state_dict(ref.state_dict())
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    ob = O.collate(graphs)
+    out_r = ref(ob)
+    y = ob["y"].float()
+    loss_r = torch.nn.functional.l1_loss(out_r, y.expand_as(out_r), reduction="sum")
+    loss_r.backward()
+    model = model.to(dev())
+    hb = collate(graphs).to(dev())
+    out = model(hb)
+    loss = torch.nn.functional.l1_loss(out, hb.y.float().expand_as(out), reduction="sum")
+    loss.backward()
+    assert_close(out, out_r, rtol=2e-5, name="model out")
+    assert_close(loss, loss_r, rtol=2e-5, name="loss")
+    for (k, p), (_, pr) in zip(model.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, pr.grad, rtol=1e-4, name="grad " + k)     # 4-5 layers deep: 1e-4 on grads
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt_r = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    opt.step()
+    opt_r.step()
+    for (k, p), (_, pr) in zip(model.named_parameters(), ref.named_parameters()):
+        assert_close(p, pr, rtol=1e-4, name="param after Adam " + k)
