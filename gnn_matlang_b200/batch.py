@@ -28,6 +28,16 @@ class Batch(object):
             out.batch._gnnml3_ptr = (out.batch._version, out.graph_ptr)
         return out
 
+    def fresh(self):
+        """New tensor objects over the same storage: drops the per-tensor caches (graph plan, sorted edge
+        features), i.e. what a training loop sees when every step brings a new batch."""
+        out = Batch()
+        for k, v in self.__dict__.items():
+            out.__dict__[k] = v.detach() if isinstance(v, torch.Tensor) else v
+        if getattr(out, "batch", None) is not None and getattr(out, "graph_ptr", None) is not None and out.batch.is_cuda:
+            out.batch._gnnml3_ptr = (out.batch._version, out.graph_ptr)
+        return out
+
     def pin_memory(self):
         out = Batch()
         for k, v in self.__dict__.items():
@@ -42,7 +52,7 @@ def collate(graphs):
     """``graphs``: sequence of dicts / objects with ``x [n,f]``, ``edge_index2 [2,e]``, ``edge_attr2 [e,K]``
     and optionally ``y``.  Returns a host ``Batch``."""
     def get(g, k):
-        return g[k] if isinstance(g, dict) else getattr(g, k, None)
+        return g.get(k) if isinstance(g, dict) else getattr(g, k, None)
 
     ns = np.array([int(get(g, "x").shape[0]) for g in graphs], dtype=np.int64)
     off = np.zeros(len(graphs) + 1, dtype=np.int64)

@@ -11,6 +11,15 @@ import torch
 from . import ops
 
 
+_RANGE_CHECK = [True]
+
+
+def set_range_check(flag):
+    """The index range check reads one flag back from the device (a host sync per new batch); trusted
+    pipelines (our own collation) switch it off."""
+    _RANGE_CHECK[0] = bool(flag)
+
+
 class GraphPlan(object):
     __slots__ = ("N", "E", "rowptr", "col", "perm", "rowptrT", "colT", "permT", "device")
 
@@ -27,7 +36,7 @@ def get_plan(edge_index, num_nodes):
     cached = getattr(edge_index, "_gnnml3_plan", None)
     if cached is not None and cached[0] == edge_index._version and cached[1].N == int(num_nodes):
         return cached[1]
-    plan = GraphPlan(edge_index, num_nodes)
+    plan = GraphPlan(edge_index, num_nodes, check_range=_RANGE_CHECK[0])
     try:
         edge_index._gnnml3_plan = (edge_index._version, plan)
     except Exception:  # pragma: no cover - tensors that refuse attributes just rebuild each call

@@ -260,3 +260,43 @@ def segment_pool_bwd(gout, graph_ptr, mean, N):
         _lib.check(lib.gnnml3_segment_pool_bwd(_lib.ptr(gout), _lib.ptr(graph_ptr), B, F, int(mean), _lib.ptr(gx), _ld(gx),
                                                _lib.stream_ptr()), "gnnml3_segment_pool_bwd")
     return gx
+
+
+# --------------------------------------------------------------------------------------------------
+# optional per-call device timing (CUDA events on the launching stream) used by bench.py
+# --------------------------------------------------------------------------------------------------
+_prof = {"enabled": False, "names": None, "records": []}
+
+
+def profile_start(names=None):
+    _prof["enabled"], _prof["names"], _prof["records"] = True, (set(names) if names else None), []
+
+
+def profile_stop():
+    """-> list of (name, milliseconds, shapes); synchronises the device."""
+    _prof["enabled"] = False
+    torch.cuda.synchronize()
+    out = [(n, s.elapsed_time(e), shp) for n, s, e, shp in _prof["records"]]
+    _prof["records"] = []
+    return out
+
+
+def _instrument(name, fn):
+    def wrapped(*a, **k):
+        if not _prof["enabled"] or (_prof["names"] is not None and name not in _prof["names"]):
+            return fn(*a, **k)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn(*a, **k)
+        e.record()
+        shapes = tuple(tuple(t.shape) for t in a if isinstance(t, torch.Tensor))
+        _prof["records"].append((name, s, e, shapes))
+        return out
+    wrapped.__name__ = fn.__name__
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+
+
+for _n in ("csr_build", "gather_rows", "scatter_rows", "spmm_k", "sddmm_k", "gemm_nn", "gemm_tn", "colsum", "edge_mlp_fwd",
+           "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "segment_pool_fwd", "segment_pool_bwd"):
+    globals()[_n] = _instrument(_n, globals()[_n])

@@ -1,0 +1,158 @@
+"""CPU tests of the host-side logic: C-ABI surface, batching, synthetic shapes, data-parallel step (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import gnnml3_oracle as O
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "gnnml3_b200.h")).read()
+    return sorted(set(re.findall(r"GNNML3_API\s+[\w\s\*]+?\b(gnnml3_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gnn_matlang_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    assert sorted(_lib.SIGNATURES.keys()) == syms                      # the ctypes binding covers the whole header
+    lib = ctypes.CDLL(_lib.LIB_PATH)                                   # built by __graft_entry__.build()
+    for s in syms:
+        assert hasattr(lib, s), s
+    _lib.load()
+    assert _lib.load().gnnml3_version() >= 100
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l and "gnnml3_" in l)
+    assert exported == syms                                            # nothing undeclared leaks out either
+
+
+def test_library_is_sm100a_only():
+    from gnn_matlang_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_product_never_imports_the_oracle():
+    for dp, _, fs in os.walk(os.path.join(ROOT, "gnn_matlang_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("the oracle", ""), os.path.join(dp, f)
+
+
+def test_cpu_tensors_raise_no_fallback():
+    from gnn_matlang_b200.libs.spect_conv import SpectConv, ML3Layer
+    m = SpectConv(4, 4, 2, selfconn=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(5, 4), torch.randint(0, 5, (2, 9)), torch.randn(9, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ML3Layer(True, 2, 2, 4, 4, 2)(torch.randn(5, 4), torch.randint(0, 5, (2, 9)), torch.randn(9, 2))
+
+
+def test_module_surface_matches_reference():
+    from gnn_matlang_b200.libs.spect_conv import SpectConv, ML3Layer
+    m = SpectConv(5, 7, K=3)                                          # selfconn defaults to True (reference :26)
+    assert m.weight.shape == (4, 5, 7) and m.bias.shape == (7,) and repr(m) == "SpectConv(5, 7, K=4)"
+    assert float(m.bias.abs().max()) == 0 and float(m.weight.abs().max()) <= (6.0 / 12) ** 0.5
+    d = SpectConv(5, 7, K=3, selfconn=True, depthwise=True, bias=False)
+    assert d.DSweight.shape == (4, 5) and d.weight.shape == (1, 5, 7) and d.bias is None and d.nsup == 4
+    assert float(d.DSweight.abs().max()) == 0
+    l = ML3Layer(True, 6, 6, 2, 32, 16)
+    assert [k for k, _ in l.named_parameters()] == [k for k, _ in O.OracleML3Layer(True, 6, 6, 2, 32, 16).named_parameters()]
+    assert [tuple(p.shape) for p in l.parameters()] == [tuple(p.shape) for p in O.OracleML3Layer(True, 6, 6, 2, 32, 16).parameters()]
+    # identical RNG consumption => identical initial weights under the same seed (graph8c.py:284 relies on this)
+    torch.manual_seed(3)
+    a = ML3Layer(True, 6, 6, 2, 32, 16)
+    torch.manual_seed(3)
+    b = O.OracleML3Layer(True, 6, 6, 2, 32, 16)
+    for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(p, q), k
+
+
+def test_collate_is_bit_exact_with_the_oracle():
+    from gnn_matlang_b200.batch import collate
+    from gnn_matlang_b200.synthetic import GraphPool
+    rng = np.random.default_rng(0)
+    pool = GraphPool("zinc", 40, seed=3)
+    idx = rng.integers(0, 40, 17)
+    recs = []
+    for i in idx:
+        ns, ne = slice(pool.node_off[i], pool.node_off[i + 1]), slice(pool.edge_off[i], pool.edge_off[i + 1])
+        recs.append(dict(x=pool.x[ns], edge_index2=pool.ei2[:, ne], edge_attr2=pool.ea2[ne], y=pool.y[i]))
+    a, b, c = collate(recs), O.collate(recs), pool.collate(idx)
+    for k in ("x", "edge_index2", "edge_attr2", "batch"):
+        assert torch.equal(getattr(a, k), b[k]), k
+        assert torch.equal(getattr(c, k), b[k]), k
+    assert a.edge_index2.dtype == torch.int64 and a.num_graphs == 17
+    assert torch.equal(a.graph_ptr.long(), torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(a.batch).cumsum(0)]))
+    assert torch.equal(c.y.flatten(), b["y"].flatten().float())
+    # batched edge list stays sorted by (src, dst)
+    key = a.edge_index2[0] * a.x.shape[0] + a.edge_index2[1]
+    assert bool((key[1:] > key[:-1]).all())
+
+
+@pytest.mark.parametrize("kind,kw", [("zinc", dict(recfield=2, dv=2, nfreq=7)),
+                                     ("counting", dict(recfield=1, dv=1, nfreq=10, adddegree=True, laplacien=False, addadj=True)),
+                                     ("sweep", dict(recfield=1, dv=5, nfreq=9))])
+def test_synthetic_masks_match_spectral_design(kind, kw):
+    from gnn_matlang_b200 import synthetic as S
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        n, ei, x = dict(zinc=S.zinc_graph, counting=S.counting_graph, sweep=lambda r: S.sweep_graph(r, 4))[kind](rng)
+        with np.errstate(all="ignore"):
+            d = O.spectral_design(ei, x[:, :1], **kw)
+        assert np.array_equal(S.mask_edges(n, ei, kw["recfield"]), d["edge_index2"])
+        assert d["edge_attr2"].shape[1] == dict(zinc=8, counting=12, sweep=10)[kind]
+        assert np.array_equal(ei, ei[:, np.lexsort((ei[1], ei[0]))])
+
+
+def _dp_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    from gnn_matlang_b200.synthetic import GraphPool
+    from gnn_matlang_b200.train import Trainer
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    pool = GraphPool("zinc", 16, seed=0)
+
+    class Adapter(torch.nn.Module):                  # the oracle model stands in for the CUDA model on CPU
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.m = O.OracleGNNML3("zinc", 8, 25)
+
+        def forward(self, b):
+            return self.m(dict(x=b.x, edge_index2=b.edge_index2, edge_attr2=b.edge_attr2, batch=b.batch, num_graphs=b.num_graphs))
+
+    idx = np.arange(8)
+    shard = idx[rank * 4:(rank + 1) * 4]             # contiguous chunk of whole graphs per rank
+    tr = Trainer(Adapter(), loss="l1", distributed=True)
+    for _ in range(2):
+        tr.step(pool.collate(shard))
+    if rank == 0:
+        single = Trainer(Adapter(), loss="l1", distributed=False)
+        for _ in range(2):
+            single.step(pool.collate(idx))
+        torch.save([[p.detach().clone() for p in tr.model.parameters()], [p.detach().clone() for p in single.model.parameters()]], tmp)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_equals_single_process(tmp_path):
+    """world_size 2 over gloo: graphs sharded across ranks + SUM all-reduce of the flat gradient == one process
+    on the whole minibatch (every loss of the reference is reduction='sum')."""
+    import torch.multiprocessing as mp
+    tmp = str(tmp_path / "dp.pt")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_dp_worker, args=(2, port, tmp), nprocs=2, join=True)
+    dp, single = torch.load(tmp)
+    for a, b in zip(dp, single):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
