@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-graphs", type=int, default=2048, help="graphs per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
     return ap.parse_args()
 
 
@@ -226,14 +227,16 @@ def main():
                     "algorithmic_bytes_per_launch": sp_bytes / len(recs)}
 
     # ---- kernel breakdown pass (separate, untimed): share of every library call
-    ops.profile_start()
-    for i in range(2):
-        trainer.step(dev_ring[i % args.ring].fresh())
-    recs_all = ops.profile_stop()
-    agg = {}
-    for n, m, _ in recs_all:
-        agg[n] = agg.get(n, 0.0) + m / 2
-    breakdown = {k: round(v, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
+    breakdown = None
+    if not args.no_breakdown:
+        ops.profile_start()
+        for i in range(2):
+            trainer.step(dev_ring[i % args.ring].fresh())
+        recs_all = ops.profile_stop()
+        agg = {}
+        for n, m, _ in recs_all:
+            agg[n] = agg.get(n, 0.0) + m / 2
+        breakdown = {k: round(v, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
 
     # ---- end to end: host (pinned) batches through Trainer; H2D of every step's inputs + D2H of the loss inside
     e2e = None

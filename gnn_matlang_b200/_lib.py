@@ -42,6 +42,10 @@ SIGNATURES = {
     "gnnml3_ml3_act_bwd": (_i, [_p, _i64, _p, _i64, _i64, _i, _i, _p, _i64, _p, _i64, _p]),
     "gnnml3_segment_pool_fwd": (_i, [_p, _i64, _p, _i, _i, _i, _p, _p]),
     "gnnml3_segment_pool_bwd": (_i, [_p, _p, _i, _i, _i, _p, _i64, _p]),
+    "gnnml3_spectral_max_nodes": (_i, [_i]),
+    "gnnml3_spectral_count": (_i, [_p, _i64, _p, _p, _i, _i, _i, _p, _p]),
+    "gnnml3_spectral_design": (_i, [_p, _i64, _p, _p, _i, _i, ctypes.c_double, _i, _i, _i, _i, ctypes.c_double, _i, _p, _i, _p,
+                                    _i64, _p, _p, _p, _p]),
 }
 
 PREC_3XTF32 = 0

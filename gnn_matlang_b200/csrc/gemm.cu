@@ -36,10 +36,10 @@ __device__ __forceinline__ void split_tf32(const float (&v)[N], uint32_t (&hi)[N
     }
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+// 16-byte cp.async that reads only the first `bytes` (0..16) from global memory and zero-fills the rest
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int bytes) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -62,9 +62,10 @@ __device__ __forceinline__ void load_tile(float* __restrict__ s, const float* __
 #pragma unroll
         for (int i = threadIdx.x; i < TOTAL; i += THREADS) {
             const int r = i / CV, c = (i % CV) * 4;
-            const bool ok = (r0 + r < rmax) && (c0 + c < cmax);
-            const float* src = ok ? g + (r0 + r) * ld + c0 + c : g;
-            cp_async16(s + r * LDS + c, src, ok);
+            int nb = (r0 + r < rmax) ? (cmax - (c0 + c)) * 4 : 0;     // rows need 16-byte alignment only; the row
+            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);                    // tail is a partial vector (zero-filled)
+            const float* src = nb > 0 ? g + (r0 + r) * ld + c0 + c : g;
+            cp_async16(s + r * LDS + c, src, nb);
         }
     } else {
         constexpr int TOTAL = ROWS * COLS;
@@ -86,7 +87,7 @@ constexpr size_t nn_smem_bytes() {
     return sizeof(float) * NN_STAGES * (NN_BM * NN_LDA + NN_BK * (BN + 8));
 }
 
-template <int BN, bool VEC16, bool X3>
+template <int BN, bool VA, bool VB, bool X3>
 __global__ void __launch_bounds__(NN_THREADS)
 k_gemm_nn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
           const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int Nc, int Kc, int epi) {
@@ -113,8 +114,8 @@ k_gemm_nn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 
     auto issue = [&](int kt) {
         const int st = kt % NN_STAGES;
-        load_tile<NN_BM, NN_BK, NN_LDA, NN_THREADS, VEC16>(As + st * NN_BM * NN_LDA, A, lda, m0, kt * NN_BK, M, Kc);
-        load_tile<NN_BK, BN, LDB, NN_THREADS, VEC16>(Bs + st * NN_BK * LDB, B, ldb, (int64_t)kt * NN_BK, n0, Kc, Nc);
+        load_tile<NN_BM, NN_BK, NN_LDA, NN_THREADS, VA>(As + st * NN_BM * NN_LDA, A, lda, m0, kt * NN_BK, M, Kc);
+        load_tile<NN_BK, BN, LDB, NN_THREADS, VB>(Bs + st * NN_BK * LDB, B, ldb, (int64_t)kt * NN_BK, n0, Kc, Nc);
     };
 #pragma unroll
     for (int s = 0; s < NN_STAGES - 1; ++s) {
@@ -225,7 +226,7 @@ k_gemm_nn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 constexpr int TN_BA = 64, TN_BB = 64, TN_BK = 32, TN_STAGES = 3, TN_THREADS = 128, TN_LD = 72;
 constexpr size_t tn_smem_bytes() { return sizeof(float) * TN_STAGES * TN_BK * TN_LD * 2; }
 
-template <bool VEC16, bool X3>
+template <bool VA, bool VB, bool X3>
 __global__ void __launch_bounds__(TN_THREADS)
 k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ P,
           int64_t M, int Ka, int Nb, int64_t rows_per_split) {
@@ -250,8 +251,8 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 
     auto issue = [&](int kt) {
         const int st = kt % TN_STAGES;
-        load_tile<TN_BK, TN_BA, TN_LD, TN_THREADS, VEC16>(As + st * TN_BK * TN_LD, A, lda, mbeg + (int64_t)kt * TN_BK, a0, mend, Ka);
-        load_tile<TN_BK, TN_BB, TN_LD, TN_THREADS, VEC16>(Bs + st * TN_BK * TN_LD, B, ldb, mbeg + (int64_t)kt * TN_BK, b0, mend, Nb);
+        load_tile<TN_BK, TN_BA, TN_LD, TN_THREADS, VA>(As + st * TN_BK * TN_LD, A, lda, mbeg + (int64_t)kt * TN_BK, a0, mend, Ka);
+        load_tile<TN_BK, TN_BB, TN_LD, TN_THREADS, VB>(Bs + st * TN_BK * TN_LD, B, ldb, mbeg + (int64_t)kt * TN_BK, b0, mend, Nb);
     };
 #pragma unroll
     for (int s = 0; s < TN_STAGES - 1; ++s) {
@@ -358,7 +359,7 @@ static void tn_plan(int64_t M, int Ka, int Nb, int* splits, int64_t* rows_per_sp
 }
 
 // ------------------------------------------------------------------------------------------------ colsum
-constexpr int CS_ROWS = 2048;
+constexpr int CS_ROWS = 256;
 __global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict__ A, int64_t lda, int64_t M, int Nc,
                                                         float* __restrict__ P) {
     __shared__ float red[8][33];
@@ -386,19 +387,28 @@ __global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict_
 
 using namespace gnnml3;
 
-template <int BN, bool VEC16, bool X3>
+template <int BN, bool VA, bool VB, bool X3>
 static int launch_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                      int64_t M, int Nc, int Kc, int epi, cudaStream_t st) {
     static bool configured = false;  // benign race: the attribute call is idempotent
     if (!configured) {
-        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_nn<BN, VEC16, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_nn<BN, VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)nn_smem_bytes<BN>()));
         configured = true;
     }
     dim3 grid(cdiv(M, NN_BM), cdiv(Nc, BN));
-    k_gemm_nn<BN, VEC16, X3><<<grid, NN_THREADS, nn_smem_bytes<BN>(), st>>>(A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epi);
+    k_gemm_nn<BN, VA, VB, X3><<<grid, NN_THREADS, nn_smem_bytes<BN>(), st>>>(A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epi);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
+}
+
+template <int BN, bool X3>
+static int launch_nn_v(bool va, bool vb, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                       int64_t ldc, int64_t M, int Nc, int Kc, int epi, cudaStream_t st) {
+    if (va && vb) return launch_nn<BN, true, true, X3>(A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epi, st);
+    if (va) return launch_nn<BN, true, false, X3>(A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epi, st);
+    if (vb) return launch_nn<BN, false, true, X3>(A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epi, st);
+    return launch_nn<BN, false, false, X3>(A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epi, st);
 }
 
 extern "C" int gnnml3_gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
@@ -410,18 +420,16 @@ extern "C" int gnnml3_gemm_nn(const float* A, int64_t lda, const float* B, int64
     GNNML3_REQUIRE(epilogue == GNNML3_EPI_NONE || epilogue == GNNML3_EPI_RELU, "gemm_nn: unknown epilogue %d", epilogue);
     GNNML3_REQUIRE(cdiv(M, NN_BM) > 0 && cdiv(Nc, 32) < 65536, "gemm_nn: grid too large");
     cudaStream_t st = (cudaStream_t)stream_;
-    const bool v16 = lda % 4 == 0 && ldb % 4 == 0 && Kc % 4 == 0 && Nc % 4 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0;
+    // 128-bit loads need 16-byte aligned rows only (partial vectors at the row tail are zero-filled)
+    const bool va = (lda % 4 == 0 || M == 1) && (uintptr_t)A % 16 == 0;
+    const bool vb = (ldb % 4 == 0 || Kc == 1) && (uintptr_t)B % 16 == 0;
     const bool x3 = precision == GNNML3_PREC_3XTF32;
-    const bool wide = Nc > 32;
-#define NN_GO(BN, V, X) return launch_nn<BN, V, X>(A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epilogue, st)
-    if (wide) {
-        if (v16) { if (x3) NN_GO(64, true, true); else NN_GO(64, true, false); }
-        else     { if (x3) NN_GO(64, false, true); else NN_GO(64, false, false); }
-    } else {
-        if (v16) { if (x3) NN_GO(32, true, true); else NN_GO(32, true, false); }
-        else     { if (x3) NN_GO(32, false, true); else NN_GO(32, false, false); }
+    if (Nc > 32) {
+        return x3 ? launch_nn_v<64, true>(va, vb, A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epilogue, st)
+                  : launch_nn_v<64, false>(va, vb, A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epilogue, st);
     }
-#undef NN_GO
+    return x3 ? launch_nn_v<32, true>(va, vb, A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epilogue, st)
+              : launch_nn_v<32, false>(va, vb, A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epilogue, st);
 }
 
 extern "C" size_t gnnml3_gemm_tn_workspace_bytes(int64_t M, int Ka, int Nb) {
@@ -431,18 +439,27 @@ extern "C" size_t gnnml3_gemm_tn_workspace_bytes(int64_t M, int Ka, int Nb) {
     return align_up((size_t)splits * Ka * Nb * sizeof(float), 256);
 }
 
-template <bool VEC16, bool X3>
+template <bool VA, bool VB, bool X3>
 static int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb,
                      int splits, int64_t rps, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn<VEC16, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem_bytes()));
+        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn<VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem_bytes()));
         configured = true;
     }
     dim3 grid(cdiv(Ka, TN_BA), cdiv(Nb, TN_BB), splits);
-    k_gemm_tn<VEC16, X3><<<grid, TN_THREADS, tn_smem_bytes(), st>>>(A, lda, B, ldb, P, M, Ka, Nb, rps);
+    k_gemm_tn<VA, VB, X3><<<grid, TN_THREADS, tn_smem_bytes(), st>>>(A, lda, B, ldb, P, M, Ka, Nb, rps);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
+}
+
+template <bool X3>
+static int launch_tn_v(bool va, bool vb, const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka,
+                       int Nb, int splits, int64_t rps, cudaStream_t st) {
+    if (va && vb) return launch_tn<true, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (va) return launch_tn<true, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (vb) return launch_tn<false, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    return launch_tn<false, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
 }
 
 extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
@@ -459,14 +476,11 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
     int64_t rps;
     tn_plan(M, Ka, Nb, &splits, &rps);
     cudaStream_t st = (cudaStream_t)stream_;
-    const bool v16 = lda % 4 == 0 && ldb % 4 == 0 && Ka % 4 == 0 && Nb % 4 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0;
-    const bool x3 = precision == GNNML3_PREC_3XTF32;
+    const bool va = (lda % 4 == 0 || M == 1) && (uintptr_t)A % 16 == 0;
+    const bool vb = (ldb % 4 == 0 || M == 1) && (uintptr_t)B % 16 == 0;
     float* P = (float*)workspace;
-    int rc;
-    if (v16) rc = x3 ? launch_tn<true, true>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
-                     : launch_tn<true, false>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
-    else     rc = x3 ? launch_tn<false, true>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
-                     : launch_tn<false, false>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    const int rc = precision == GNNML3_PREC_3XTF32 ? launch_tn_v<true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
+                                                   : launch_tn_v<false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
     if (rc) return rc;
     const int64_t n = (int64_t)Ka * Nb;
     k_reduce_partials<<<cdiv(n, 256) > 1184 ? 1184 : cdiv(n, 256), 256, 0, st>>>(P, splits, n, Nb, C, ldc);

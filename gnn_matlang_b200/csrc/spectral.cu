@@ -136,7 +136,6 @@ __device__ void jacobi_eigh(double* As, double* Us, int n, int ld, double* cs, d
                 }
                 cs[4 * tid + 0] = c;
                 cs[4 * tid + 1] = s;
-                cs[4 * tid + 2] = __int_as_float(0);   // keep layout simple: p, q stored as doubles below
                 cs[4 * tid + 2] = (double)p;
                 cs[4 * tid + 3] = (double)q;
             }

@@ -81,30 +81,44 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ col, const int* _
             for (int v = 0; v < VEC; ++v) acc[k][c][v] = 0.f;
 
     const int rs = __ldg(rowptr + row), re = __ldg(rowptr + row + 1);
-    int s_next = 0, e_next = 0;
-    if (rs < re) {
-        s_next = __ldg(col + rs);
-        e_next = eperm ? __ldg(eperm + rs) : rs;
-    }
-    for (int p = rs; p < re; ++p) {
-        const int s = s_next, e = e_next;
-        if (p + 1 < re) {  // prefetch the next edge's indices so its gathers can issue early
-            s_next = __ldg(col + p + 1);
-            e_next = eperm ? __ldg(eperm + p + 1) : p + 1;
+    // U edges per iteration: all index, weight and source-row loads of the U edges are issued before the first FMA,
+    // so a lane keeps U * (CH + K/WV) independent 64/128-bit loads in flight (rows are short -- 5..20 edges -- and
+    // the index -> gather chain would otherwise serialise on memory latency).  Edges past the end of the row are
+    // predicated off with zero weights.
+    constexpr int U = (K * VEC * CH <= 32) ? 4 : 2;
+    for (int p0 = rs; p0 < re; p0 += U) {
+        int sidx[U], eidx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = min(p0 + u, re - 1);
+            sidx[u] = __ldg(col + p);
+            eidx[u] = eperm ? __ldg(eperm + p) : p;
         }
-        float w[K];
-        load_weights<K, WV>(ea + (int64_t)e * Kstride, w);
-        const float* xr = x + (int64_t)s * ldx;
+        float w[U][K], xv[U][CH][VEC];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const int f0 = (c * G + g) * VEC;
-            if (f0 < F) {
-                float xv[VEC];
-                load_vec<VEC>(xr + f0, xv);
+        for (int u = 0; u < U; ++u) {
+            load_weights<K, WV>(ea + (int64_t)eidx[u] * Kstride, w[u]);
+            const float* xr = x + (int64_t)sidx[u] * ldx;
 #pragma unroll
-                for (int k = 0; k < K; ++k)
+            for (int c = 0; c < CH; ++c) {
+                const int f0 = (c * G + g) * VEC;
+                if (f0 < F) {
+                    load_vec<VEC>(xr + f0, xv[u][c]);
+                } else {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[k][c][v] = fmaf(w[k], xv[v], acc[k][c][v]);
+                    for (int v = 0; v < VEC; ++v) xv[u][c][v] = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p0 + u < re) {       // keeps the reference's summation order: edges of a row in original order
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[k][c][v] = fmaf(w[u][k], xv[u][c][v], acc[k][c][v]);
             }
         }
     }
@@ -156,11 +170,25 @@ k_sddmm(const int* __restrict__ rowptr, const int* __restrict__ col, const int* 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
 
+    // where this lane's fully reduced values land after the reduce-scatter below
+    constexpr int KP = K <= 1 ? 1 : (K <= 2 ? 2 : (K <= 4 ? 4 : 8));
+    int kbase = 0, lowmask = 0, nkeep = KP;
+    {
+        int o = G >> 1, h = KP >> 1;
+        while (h >= 1 && o >= 1) {
+            if (g & o) kbase += h;
+            nkeep = h;
+            h >>= 1;
+            o >>= 1;
+        }
+        if (o >= 1) lowmask = 2 * o - 1;
+    }
+
     for (int i = 0; i < maxcnt; ++i) {
         const bool act = i < cnt;
-        float part[K];
+        float part[KP];
 #pragma unroll
-        for (int k = 0; k < K; ++k) part[k] = 0.f;
+        for (int k = 0; k < KP; ++k) part[k] = 0.f;
         int e = 0;
         if (act) {
             const int p = rs + i;
@@ -180,16 +208,30 @@ k_sddmm(const int* __restrict__ rowptr, const int* __restrict__ col, const int* 
                 }
             }
         }
+        // reduce-scatter over the G lanes of the row: every step halves the number of live values per lane
+        // (K/2 + K/4 + ... shuffles instead of K log2 G); once one value is left the remaining steps are plain adds
+        {
+            int o = G >> 1;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            float v = part[k];
-            for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            part[k] = v;
+            for (int h = KP >> 1; h >= 1; h >>= 1) {
+                if (o >= 1) {
+                    const bool upper = (g & o) != 0;
+#pragma unroll
+                    for (int q = 0; q < h; ++q) {
+                        const float keep = upper ? part[q + h] : part[q];
+                        const float send = upper ? part[q] : part[q + h];
+                        part[q] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                    o >>= 1;
+                }
+            }
+            for (; o >= 1; o >>= 1) part[0] += __shfl_xor_sync(0xffffffffu, part[0], o);
         }
-        if (act && g == 0) {
-            float* o = dea + (int64_t)e * Kstride;
+        if (act && (g & lowmask) == 0) {
+            float* o = dea + (int64_t)e * Kstride + kbase;
 #pragma unroll
-            for (int k = 0; k < K; ++k) o[k] = part[k];
+            for (int q = 0; q < KP; ++q)
+                if (q < nkeep && kbase + q < K) o[q] = part[q];
         }
     }
 }

@@ -1,0 +1,106 @@
+"""Drop-in replacement for the reference's ``libs/utils.py::SpectralDesign`` (libs/utils.py:525-626):
+
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    transform = SpectralDesign(nmax=0, recfield=1, dv=5, nfreq=5, adddegree=False, laplacien=True, addadj=False, vmax=None)
+    data = transform(data)          # adds edge_index2, edge_attr2, lmax; augments x if adddegree
+
+Same constructor arguments and the same ``__call__(data) -> data`` contract, plus a batched entry point
+(``design_batch``) that designs the supports of many graphs in one launch -- one CUDA thread block per graph,
+FP64 Jacobi eigensolver in shared memory (the reference loops over graphs in Python with one dense numpy
+``eigh`` each).  The PPGN tensors ``X2`` / ``M`` that the reference also builds when ``nmax > 0``
+(:613-624) are not read by GNNML3 and are not produced (``nmax`` is accepted and ignored).
+No CPU fallback: a CUDA device is required.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def get_n_params(model):
+    """libs/utils.py:14-21"""
+    return sum(p.numel() for p in model.parameters())
+
+
+class SpectralDesign(object):
+
+    def __init__(self, nmax=0, recfield=1, dv=5, nfreq=5, adddegree=False, laplacien=True, addadj=False, vmax=None):
+        self.recfield = recfield        # receptive field. 0: adj, 1: adj+I, r: 2^(r-1)-hop area
+        self.dv = dv                    # bandwidth of the Gaussian band filters
+        self.nfreq = nfreq              # number of sampled points of the spectrum
+        self.adddegree = adddegree      # append the node degree to the node features
+        self.laplacien = laplacien      # spectrum of the normalised Laplacian (True) or of the adjacency (False)
+        self.addadj = addadj            # add the adjacency as one more edge feature
+        self.vmax = vmax                # use the given maximum eigenvalue
+        self.nmax = nmax                # PPGN only; ignored here
+
+    @property
+    def num_supports(self):
+        return self.nfreq + 1 + (1 if self.addadj else 0)
+
+    # ------------------------------------------------------------------------------------------ batched
+    def design_batch(self, edge_index, edge_ptr, node_ptr, device=None, global_ids=False):
+        """edge_index [2, Etot] int64 with LOCAL node ids, edge_ptr / node_ptr [B+1] (any int dtype, any device).
+        Returns a dict of device tensors: edge_index2 [2, E2], edge_attr2 [E2, K], e2_ptr [B+1] (int64),
+        lmax [B], degree [Ntot]."""
+        lib = _lib.load()
+        if device is None:
+            device = edge_index.device if edge_index.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if not torch.cuda.is_available():
+            raise RuntimeError("gnn_matlang_b200.SpectralDesign needs a CUDA device (no CPU fallback)")
+        node_ptr_h = torch.as_tensor(node_ptr).to("cpu", torch.int64)
+        B = node_ptr_h.numel() - 1
+        nmax = int((node_ptr_h[1:] - node_ptr_h[:-1]).max()) if B > 0 else 1
+        ei = torch.as_tensor(edge_index).to(device=device, dtype=torch.int64).contiguous()
+        ep = torch.as_tensor(edge_ptr).to(device=device, dtype=torch.int32).contiguous()
+        npd = node_ptr_h.to(device=device, dtype=torch.int32).contiguous()
+        Etot, Ntot = ei.size(1), int(node_ptr_h[-1]) if B > 0 else 0
+        K = self.num_supports
+        counts = torch.zeros(B, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            st = _lib.stream_ptr()
+            _lib.check(lib.gnnml3_spectral_count(_lib.ptr(ei), Etot, _lib.ptr(ep), _lib.ptr(npd), B, int(self.recfield),
+                                                 max(nmax, 1), _lib.ptr(counts), st), "gnnml3_spectral_count")
+            e2_ptr = torch.zeros(B + 1, dtype=torch.int64, device=device)
+            torch.cumsum(counts, 0, out=e2_ptr[1:])
+            E2 = int(e2_ptr[-1].item()) if B > 0 else 0
+            ei2 = torch.empty(2, E2, dtype=torch.int64, device=device)
+            ea2 = torch.empty(E2, K, dtype=torch.float32, device=device)
+            lmax = torch.zeros(B, dtype=torch.float32, device=device)
+            deg = torch.zeros(Ntot, dtype=torch.float32, device=device)
+            _lib.check(lib.gnnml3_spectral_design(
+                _lib.ptr(ei), Etot, _lib.ptr(ep), _lib.ptr(npd), B, int(self.recfield), float(self.dv), int(self.nfreq),
+                int(bool(self.laplacien)), int(bool(self.addadj)), int(self.vmax is not None),
+                float(self.vmax if self.vmax is not None else 0.0), max(nmax, 1), _lib.ptr(e2_ptr), int(bool(global_ids)),
+                _lib.ptr(ei2), E2, _lib.ptr(ea2), _lib.ptr(lmax), _lib.ptr(deg), st), "gnnml3_spectral_design")
+        return dict(edge_index2=ei2, edge_attr2=ea2, e2_ptr=e2_ptr, lmax=lmax, degree=deg)
+
+    def design_list(self, graphs, device=None):
+        """``graphs``: list of (n, edge_index [2,e]) pairs -> per-graph list of dicts (edge_index2, edge_attr2,
+        lmax, degree), all designed in one launch."""
+        ns = np.array([int(n) for n, _ in graphs], dtype=np.int64)
+        es = np.array([int(np.asarray(e).shape[1]) for _, e in graphs], dtype=np.int64)
+        node_ptr = np.concatenate([[0], np.cumsum(ns)])
+        edge_ptr = np.concatenate([[0], np.cumsum(es)])
+        ei = np.concatenate([np.asarray(e, dtype=np.int64).reshape(2, -1) for _, e in graphs], 1) if len(graphs) else np.zeros((2, 0), np.int64)
+        out = self.design_batch(torch.from_numpy(ei), torch.from_numpy(edge_ptr), torch.from_numpy(node_ptr), device=device)
+        e2 = out["e2_ptr"].cpu().numpy()
+        res = []
+        for b in range(len(graphs)):
+            res.append(dict(edge_index2=out["edge_index2"][:, e2[b]:e2[b + 1]], edge_attr2=out["edge_attr2"][e2[b]:e2[b + 1]],
+                            lmax=out["lmax"][b], degree=out["degree"][node_ptr[b]:node_ptr[b + 1]]))
+        return res
+
+    # ------------------------------------------------------------------------------------------ per graph (reference API)
+    def __call__(self, data):
+        n = data.x.shape[0]
+        src_dev = data.x.device
+        data.x = data.x.type(torch.float32)
+        ei = data.edge_index
+        out = self.design_batch(ei.reshape(2, -1), torch.tensor([0, ei.reshape(2, -1).shape[1]]), torch.tensor([0, n]))
+        if self.adddegree:
+            data.x = torch.cat([data.x, out["degree"].to(src_dev).unsqueeze(-1)], 1)
+        data.lmax = np.float32(out["lmax"][0].item())
+        data.edge_index2 = out["edge_index2"].to(src_dev)
+        data.edge_attr2 = out["edge_attr2"].to(src_dev)
+        return data

@@ -135,6 +135,26 @@ GNNML3_API int gnnml3_segment_pool_fwd(const float* x, int64_t ldx, const int32_
 GNNML3_API int gnnml3_segment_pool_bwd(const float* gout, const int32_t* graph_ptr, int B, int F, int mean, float* gx,
                             int64_t ldx, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * SpectralDesign (libs/utils.py:525-610), batched: one thread block per graph, FP64 Jacobi eigensolver.
+ * Input graphs are given as concatenated LOCAL edge lists: edge_index [2, Etot] int64 (row 0 = src, row 1 = dst,
+ * node ids local to their graph), edge_ptr [B+1], node_ptr [B+1] (int32).  nmax = largest node count.
+ *   gnnml3_spectral_count : counts[b] = number of mask entries of graph b (to size the output)
+ *   gnnml3_spectral_design: writes, in the reference's row-major np.where order and at offset out_ptr[b]
+ *       (int64 exclusive scan of counts), edge_index2 [2, E2] int64 (+ node_ptr[b] if global_ids) and
+ *       edge_attr2 [E2, nfreq + 1 (+1 if addadj)] FP32; lmax [B] (max Laplacian eigenvalue, :586) and
+ *       degree [Ntot] (column sums of A, the adddegree feature, :562-563) are optional (NULL to skip).
+ *   recfield 0 -> mask A; r >= 1 -> (A + I)^(2^(r-1)) > 0.  has_vmax = 0 -> vmax = largest eigenvalue.
+ *   gnnml3_spectral_max_nodes(nfreq): largest graph the shared-memory eigensolver holds (~118).
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_spectral_max_nodes(int nfreq);
+GNNML3_API int gnnml3_spectral_count(const int64_t* edge_index, int64_t Etot, const int32_t* edge_ptr, const int32_t* node_ptr,
+                          int B, int recfield, int nmax, int32_t* counts, void* stream);
+GNNML3_API int gnnml3_spectral_design(const int64_t* edge_index, int64_t Etot, const int32_t* edge_ptr, const int32_t* node_ptr,
+                           int B, int recfield, double dv, int nfreq, int laplacien, int addadj, int has_vmax,
+                           double vmax, int nmax, const int64_t* out_ptr, int global_ids, int64_t* edge_index2,
+                           int64_t E2, float* edge_attr2, float* lmax, float* degree, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,108 @@
+"""GPU parity of SpectralDesign against fixtures produced by the UNMODIFIED reference (libs/utils.py:546-610).
+
+Edge indexing (edge_index2, the degree feature) is bit-exact.  Supports are compared AS MATRICES (they are
+invariant to eigenvector sign and to rotations inside degenerate eigenspaces): |S - S_ref| <= 1e-4*|S_ref| +
+1e-4*max|S_ref| (the north-star rtol 1e-4 with its norm-relative companion for the many near-zero entries)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN, load_npz  # noqa: E402
+from oracle import gnnml3_oracle as O  # noqa: E402
+
+SD_Z, SD_META = load_npz("spectral_design.npz")
+
+
+class _Data(object):
+    pass
+
+
+def _close_supports(ei2, ea2, ref_ei2, ref_ea2, n, rtol=1e-4):
+    a = O.supports_dense(ei2, ea2, n)
+    b = O.supports_dense(ref_ei2, ref_ea2, n)
+    tol = rtol * np.abs(b) + rtol * max(np.abs(b).max(), 1e-30)
+    assert np.all(np.abs(a - b) <= tol), "max abs err %.3e (max|ref| %.3e)" % (np.abs(a - b).max(), np.abs(b).max())
+
+
+@pytest.mark.parametrize("case", SD_META, ids=[c["name"] for c in SD_META])
+def test_spectral_design_call_matches_reference(case):
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    n = case["name"]
+    d = _Data()
+    d.x = torch.tensor(SD_Z[n + "/x"])
+    d.edge_index = torch.tensor(SD_Z[n + "/ei"])
+    out = SpectralDesign(nmax=0, **case["kw"])(d)
+    assert out.edge_index2.dtype == torch.int64 and out.edge_attr2.dtype == torch.float32
+    assert np.array_equal(out.edge_index2.numpy(), SD_Z[n + "/ei2"])                    # bit-exact
+    assert np.array_equal(out.x.numpy(), SD_Z[n + "/ox"])                               # incl. degree column
+    assert out.edge_attr2.shape == SD_Z[n + "/ea2"].shape
+    _close_supports(out.edge_index2.numpy(), out.edge_attr2.numpy(), SD_Z[n + "/ei2"], SD_Z[n + "/ea2"], d.x.shape[0])
+    np.testing.assert_allclose(out.lmax, SD_Z[n + "/lmax"], rtol=1e-5, atol=1e-6)
+    nf = case["kw"]["nfreq"]                                                            # exact 0/1 channels
+    assert np.array_equal(out.edge_attr2.numpy()[:, nf], SD_Z[n + "/ea2"][:, nf])
+    if case["kw"].get("addadj"):
+        assert np.array_equal(out.edge_attr2.numpy()[:, nf + 1], SD_Z[n + "/ea2"][:, nf + 1])
+
+
+def test_spectral_design_batched_graph8c_and_exp():
+    """All 11,117 graph8c graphs and 200 EXP graphs in one launch each vs the oracle (sampled) + invariants."""
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    g8 = O.parse_graph6(os.path.join(GOLDEN, "graph8c.g6"))
+    sd = SpectralDesign(recfield=1, dv=2, nfreq=5, adddegree=True)
+    res = sd.design_list(g8)
+    assert len(res) == 11117
+    tot = sum(r["edge_index2"].shape[1] for r in res)
+    assert tot == 409376                                                                 # SURVEY.md section 8 sizes
+    for i in list(range(0, 11117, 557)) + [11116]:
+        n, ei = g8[i]
+        ref = O.spectral_design(ei, np.ones((n, 1), np.float32), recfield=1, dv=2, nfreq=5, adddegree=True)
+        assert np.array_equal(res[i]["edge_index2"].cpu().numpy(), ref["edge_index2"])
+        assert np.array_equal(res[i]["degree"].cpu().numpy(), ref["x"][:, 1])
+        _close_supports(ref["edge_index2"], res[i]["edge_attr2"].cpu().numpy(), ref["edge_index2"], ref["edge_attr2"], n)
+    z = np.load(os.path.join(GOLDEN, "exp_first200.npz"))
+    eoff = np.concatenate([[0], np.cumsum(z["ne"])])
+    graphs = [(int(z["n"][i]), z["edge_index"][:, eoff[i]:eoff[i + 1]].astype(np.int64)) for i in range(200)]
+    res = sd.design_list(graphs)
+    for i in range(0, 200, 13):
+        n, ei = graphs[i]
+        ref = O.spectral_design(ei, np.ones((n, 1), np.float32), recfield=1, dv=2, nfreq=5, adddegree=True)
+        assert np.array_equal(res[i]["edge_index2"].cpu().numpy(), ref["edge_index2"])
+        _close_supports(ref["edge_index2"], res[i]["edge_attr2"].cpu().numpy(), ref["edge_index2"], ref["edge_attr2"], n)
+        np.testing.assert_allclose(float(res[i]["lmax"]), ref["lmax"], rtol=1e-5)
+
+
+def test_spectral_design_global_ids_equal_collation():
+    """global_ids=True emits the batched edge_index2 directly: identical to collating the per-graph outputs."""
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    from gnn_matlang_b200 import synthetic as S
+    rng = np.random.default_rng(0)
+    graphs = [S.sweep_graph(rng, 3)[:2] for _ in range(12)] + [S.zinc_graph(rng)[:2] for _ in range(12)]
+    sd = SpectralDesign(recfield=2, dv=5, nfreq=9)
+    ns = np.array([n for n, _ in graphs])
+    node_ptr = np.concatenate([[0], np.cumsum(ns)])
+    edge_ptr = np.concatenate([[0], np.cumsum([e.shape[1] for _, e in graphs])])
+    ei = np.concatenate([e for _, e in graphs], 1)
+    out = sd.design_batch(torch.from_numpy(ei), torch.from_numpy(edge_ptr), torch.from_numpy(node_ptr), global_ids=True)
+    refs = []
+    for n, e in graphs:
+        with np.errstate(all="ignore"):
+            refs.append(O.spectral_design(e, np.ones((n, 1), np.float32), recfield=2, dv=5, nfreq=9))
+    ob = O.collate(refs)
+    assert torch.equal(out["edge_index2"].cpu(), ob["edge_index2"])
+    ref_ea = ob["edge_attr2"].numpy()
+    got = out["edge_attr2"].cpu().numpy()
+    assert np.all(np.abs(got - ref_ea) <= 1e-4 * np.abs(ref_ea) + 1e-4 * np.abs(ref_ea).max())
+
+
+def test_spectral_design_rejects_oversized_graphs():
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    n = 200
+    ei = np.vstack((np.arange(n - 1), np.arange(1, n)))
+    ei = np.concatenate([ei, ei[::-1]], 1)
+    with pytest.raises(RuntimeError, match="nodes"):
+        SpectralDesign().design_list([(n, ei)])
