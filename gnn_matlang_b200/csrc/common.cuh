@@ -51,4 +51,13 @@ __device__ __forceinline__ void st_na4(float* p, float4 v) {
                  : "memory");
 }
 
+// tanh via one ex2.approx and one rcp.approx: 1 - 2 / (e^{2x} + 1), evaluated on |x| and mirrored.
+// Absolute error <= ~2e-7 over the whole range (the FP32 parity bar is 1e-5 relative to the tensor's scale);
+// ~6 instructions instead of the ~25 of tanhf -- the edge MLP evaluates 4K tanh per edge.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(2.0f * fabsf(x));
+    const float r = 1.0f - __fdividef(2.0f, e + 1.0f);
+    return copysignf(r, x);
+}
+
 }  // namespace gnnml3

@@ -104,7 +104,7 @@ k_edge_mlp_fwd(const float* __restrict__ ea, const int* __restrict__ eperm, cons
             const float a2 = dot_row<K>(sw123 + (1 * C::H + j) * C::KP, in);
             const float a3 = dot_row<K>(sw123 + (2 * C::H + j) * C::KP, in);
             tmp[j] = fmaxf(a1, 0.f);
-            tmp[C::H + j] = tanhf(a2) * tanhf(a3);
+            tmp[C::H + j] = tanh_fast(a2) * tanh_fast(a3);
         }
         float o[K];
 #pragma unroll
@@ -182,8 +182,8 @@ k_edge_mlp_bwd(const float* __restrict__ ea, const int* __restrict__ eperm, cons
                     const float a3 = dot_row<K>(sw123 + (2 * C::H + j) * C::KP, in);
                     tmp[j] = fmaxf(a1, 0.f);
                     if (a1 > 0.f) mask1 |= (1u << j);
-                    t2v[jj] = tanhf(a2);
-                    t3v[jj] = tanhf(a3);
+                    t2v[jj] = tanh_fast(a2);
+                    t3v[jj] = tanh_fast(a3);
                     tmp[C::H + j] = t2v[jj] * t3v[jj];
                 }
                 // park tanh values in the d_pre2 / d_pre3 slots until the upstream gradient is known

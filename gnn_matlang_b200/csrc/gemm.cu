@@ -336,12 +336,22 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
             }
 }
 
-__global__ void k_reduce_partials(const float* __restrict__ P, int splits, int64_t n, int cols, float* __restrict__ C,
-                                  int64_t ldc) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int z = 0; z < splits; ++z) s += P[(int64_t)z * n + i];
-        C[(i / cols) * ldc + (i % cols)] = s;
+// C[i] = sum_z P[z][i] in a fixed order: 8 split-lanes per output accumulate strided partial sums, then a fixed tree
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ P, int splits, int64_t n, int cols,
+                                                         float* __restrict__ C, int64_t ldc) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + tx;
+    float s = 0.f;
+    if (i < n)
+        for (int z = ty; z < splits; z += 8) s += __ldg(P + (int64_t)z * n + i);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < n) {
+        float v = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) v += red[y][tx];
+        C[(i / cols) * ldc + (i % cols)] = v;
     }
 }
 
@@ -483,7 +493,7 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
                                                    : launch_tn_v<false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
     if (rc) return rc;
     const int64_t n = (int64_t)Ka * Nb;
-    k_reduce_partials<<<cdiv(n, 256) > 1184 ? 1184 : cdiv(n, 256), 256, 0, st>>>(P, splits, n, Nb, C, ldc);
+    k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, splits, n, Nb, C, ldc);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
@@ -501,7 +511,7 @@ extern "C" int gnnml3_colsum(const float* A, int64_t lda, int64_t M, int Nc, flo
     const int nb = cdiv(M, CS_ROWS);
     k_colsum_partial<<<nb, 256, 0, st>>>(A, lda, M, Nc, (float*)workspace);
     GNNML3_LAUNCH_CHECK();
-    k_reduce_partials<<<cdiv(Nc, 256), 256, 0, st>>>((const float*)workspace, nb, Nc, Nc, out, Nc);
+    k_reduce_partials<<<cdiv(Nc, 32), 256, 0, st>>>((const float*)workspace, nb, Nc, Nc, out, Nc);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }

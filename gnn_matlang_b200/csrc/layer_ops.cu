@@ -30,29 +30,74 @@ __global__ void k_ml3_act_fwd(const float* __restrict__ pre, int64_t ldp, int64_
 
 // gpre[:, :Fo] = gy[:, :Fo] * (c > 0);  gpre[:, Fo+g] = gy[:, Fo+g] * t2 * (1 - t1^2);  gpre[:, Fo+G+g] = gy[:, Fo+g] * t1 * (1 - t2^2)
 // gate_out (optional) receives a second copy of the 2G gate-gradient columns (row stride ldgate).
-__global__ void k_ml3_act_bwd(const float* __restrict__ pre, int64_t ldp, const float* __restrict__ gy, int64_t ldy, int64_t N,
-                              int Fo, int G, float* __restrict__ gpre, int64_t ldg, float* __restrict__ gate_out,
-                              int64_t ldgate) {
-    const int W = Fo + G;
-    const int64_t total = N * W;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t n = i / W;
-        const int c = (int)(i - n * W);
-        const float* p = pre + n * ldp;
-        const float g = __ldg(gy + n * ldy + c);
-        if (c < Fo) {
-            gpre[n * ldg + c] = __ldg(p + c) > 0.f ? g : 0.f;
-        } else {
-            const float t1 = tanhf(__ldg(p + c)), t2 = tanhf(__ldg(p + c + G));
-            const float g1 = g * t2 * (1.f - t1 * t1), g2 = g * t1 * (1.f - t2 * t2);
-            gpre[n * ldg + c] = g1;
-            gpre[n * ldg + c + G] = g2;
-            if (gate_out) {
-                gate_out[n * ldgate + (c - Fo)] = g1;
-                gate_out[n * ldgate + (c - Fo) + G] = g2;
+// The block also accumulates the column sums of gpre over its ACT_ROWS rows (the bias gradients) and writes them to
+// colpart[block][Fo+2G]; a fixed-order second pass (k_colsum_finish) adds the blocks -- no extra pass over gpre.
+constexpr int ACT_ROWS = 128;
+__global__ void __launch_bounds__(256)
+k_ml3_act_bwd(const float* __restrict__ pre, int64_t ldp, const float* __restrict__ gy, int64_t ldy, int64_t N,
+              int Fo, int G, float* __restrict__ gpre, int64_t ldg, float* __restrict__ gate_out, int64_t ldgate,
+              float* __restrict__ colpart) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int W = Fo + G, W2 = Fo + 2 * G;
+    const int64_t r0 = (int64_t)blockIdx.x * ACT_ROWS;
+    const int64_t r1 = min(N, r0 + ACT_ROWS);
+    for (int c0 = 0; c0 < W; c0 += 32) {
+        const int c = c0 + tx;
+        float s1 = 0.f, s2 = 0.f;
+        if (c < W) {
+            for (int64_t n = r0 + ty; n < r1; n += 8) {
+                const float* p = pre + n * ldp;
+                const float g = __ldg(gy + n * ldy + c);
+                if (c < Fo) {
+                    const float v = __ldg(p + c) > 0.f ? g : 0.f;
+                    gpre[n * ldg + c] = v;
+                    s1 += v;
+                } else {
+                    const float t1 = tanhf(__ldg(p + c)), t2 = tanhf(__ldg(p + c + G));
+                    const float g1 = g * t2 * (1.f - t1 * t1), g2 = g * t1 * (1.f - t2 * t2);
+                    gpre[n * ldg + c] = g1;
+                    gpre[n * ldg + c + G] = g2;
+                    if (gate_out) {
+                        gate_out[n * ldgate + (c - Fo)] = g1;
+                        gate_out[n * ldgate + (c - Fo) + G] = g2;
+                    }
+                    s1 += g1;
+                    s2 += g2;
+                }
             }
         }
+        if (colpart) {
+            red[ty][tx] = s1;
+            __syncthreads();
+            if (ty == 0 && c < W) {
+                float v = 0.f;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) v += red[y][tx];
+                colpart[(int64_t)blockIdx.x * W2 + c] = v;
+            }
+            __syncthreads();
+            if (c >= Fo) {          // second gate column block
+                red[ty][tx] = s2;
+            }
+            __syncthreads();
+            if (ty == 0 && c >= Fo && c < W) {
+                float v = 0.f;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) v += red[y][tx];
+                colpart[(int64_t)blockIdx.x * W2 + c + G] = v;
+            }
+            __syncthreads();
+        }
     }
+}
+
+__global__ void k_colsum_finish(const float* __restrict__ part, int nblocks, int W2, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= W2) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * W2 + c];
+    out[c] = s;
 }
 
 // one warp per (graph, 32-feature chunk)
@@ -104,14 +149,35 @@ extern "C" int gnnml3_ml3_act_fwd(const float* pre, int64_t ldp, int64_t N, int 
     return GNNML3_OK;
 }
 
+extern "C" size_t gnnml3_ml3_act_bwd_workspace_bytes(int64_t N, int Fo, int G) {
+    return align_up((size_t)cdiv(N > 0 ? N : 1, ACT_ROWS) * (Fo + 2 * G) * sizeof(float), 256);
+}
+
 extern "C" int gnnml3_ml3_act_bwd(const float* pre, int64_t ldp, const float* gy, int64_t ldy, int64_t N, int Fo, int G,
-                                  float* gpre, int64_t ldg, float* gate_out, int64_t ldgate, void* stream_) {
+                                  float* gpre, int64_t ldg, float* gate_out, int64_t ldgate, float* colsum,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
     GNNML3_REQUIRE(N >= 0 && Fo >= 0 && G >= 0 && Fo + G > 0, "ml3_act_bwd: bad shape");
-    if (N == 0) return GNNML3_OK;
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (N == 0) {
+        if (colsum) GNNML3_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * (Fo + 2 * G), st));
+        return GNNML3_OK;
+    }
     GNNML3_REQUIRE(pre && gy && gpre && ldp >= Fo + 2 * G && ldy >= Fo + G && ldg >= Fo + 2 * G, "ml3_act_bwd: bad arguments");
     GNNML3_REQUIRE(gate_out == nullptr || ldgate >= 2 * G, "ml3_act_bwd: ldgate too small");
-    k_ml3_act_bwd<<<ew_grid(N * (Fo + G)), 256, 0, (cudaStream_t)stream_>>>(pre, ldp, gy, ldy, N, Fo, G, gpre, ldg, gate_out, ldgate);
+    float* part = nullptr;
+    if (colsum) {
+        GNNML3_REQUIRE(workspace, "ml3_act_bwd: workspace required for the column sums");
+        if (workspace_bytes < gnnml3_ml3_act_bwd_workspace_bytes(N, Fo, G))
+            return set_err(GNNML3_ERR_WORKSPACE, "ml3_act_bwd: workspace too small");
+        part = (float*)workspace;
+    }
+    const int nb = cdiv(N, ACT_ROWS);
+    k_ml3_act_bwd<<<nb, 256, 0, st>>>(pre, ldp, gy, ldy, N, Fo, G, gpre, ldg, gate_out, ldgate, part);
     GNNML3_LAUNCH_CHECK();
+    if (colsum) {
+        k_colsum_finish<<<cdiv(Fo + 2 * G, 128), 128, 0, st>>>(part, nb, Fo + 2 * G, colsum);
+        GNNML3_LAUNCH_CHECK();
+    }
     return GNNML3_OK;
 }
 

@@ -210,7 +210,7 @@ class _ML3LayerFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         gy = gy.contiguous()
         Gp = torch.empty(N, K * Fo + 2 * G, dtype=torch.float32, device=x.device)
-        gpre = ops.ml3_act_bwd(pre, gy, Fo, G, gate_out=Gp[:, K * Fo:] if G > 0 else None)
+        gpre, dball = ops.ml3_act_bwd(pre, gy, Fo, G, gate_out=Gp[:, K * Fo:] if G > 0 else None)
         gc = gpre[:, :Fo]
         dx = dea = None
         dws = [None, None, None, None]
@@ -232,7 +232,6 @@ class _ML3LayerFn(torch.autograd.Function):
             dx = ops.gemm_nn(Gp, torch.cat(blocks, 0).contiguous(), precision=prec)
         dcat = ops.gemm_tn(x, Gp, precision=prec)                                   # [Fi, K*Fo + 2G]
         dwc = dcat[:, :K * Fo].reshape(Fi, K, Fo).permute(1, 0, 2).contiguous()
-        dball = ops.colsum(gpre)
         if ctx.has_bias:
             dbc = dball[:Fo].contiguous()
         if G > 0:

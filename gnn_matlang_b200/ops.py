@@ -227,17 +227,21 @@ def ml3_act_fwd(pre, Fo, G):
 
 
 def ml3_act_bwd(pre, gy, Fo, G, gate_out=None):
-    """d pre [N, Fo+2G]; ``gate_out`` (a [N, >=2G] strided view) receives a copy of the gate columns."""
+    """-> (d pre [N, Fo+2G], column sums of d pre [Fo+2G] = bias gradients); ``gate_out`` (a [N, >=2G] strided
+    view) receives a copy of the gate columns."""
     lib = _lib.load()
     gy = _f32c(gy, "gy")
     N = pre.size(0)
     gpre = torch.empty(N, Fo + 2 * G, dtype=torch.float32, device=pre.device)
+    csum = torch.empty(Fo + 2 * G, dtype=torch.float32, device=pre.device)
+    ws = _ws(pre.device, lib.gnnml3_ml3_act_bwd_workspace_bytes(N, Fo, G))
     with torch.cuda.device(pre.device):
         _lib.check(lib.gnnml3_ml3_act_bwd(_lib.ptr(pre), _ld(pre), _lib.ptr(gy), _ld(gy), N, Fo, G, _lib.ptr(gpre),
                                           _ld(gpre), _lib.ptr(gate_out) if gate_out is not None else None,
-                                          _ld(gate_out) if gate_out is not None else 0, _lib.stream_ptr()),
+                                          _ld(gate_out) if gate_out is not None else 0, _lib.ptr(csum), _lib.ptr(ws),
+                                          ws.numel(), _lib.stream_ptr()),
                    "gnnml3_ml3_act_bwd")
-    return gpre
+    return gpre, csum
 
 
 def segment_pool_fwd(x, graph_ptr, mean):

@@ -123,8 +123,11 @@ GNNML3_API int gnnml3_edge_mlp_bwd(const float* ea, const int32_t* eperm, const 
  *   2G gate columns into gate_out, row stride ldgate).
  * --------------------------------------------------------------------------------------------------- */
 GNNML3_API int gnnml3_ml3_act_fwd(const float* pre, int64_t ldp, int64_t N, int Fo, int G, float* y, int64_t ldy, void* stream);
+GNNML3_API size_t gnnml3_ml3_act_bwd_workspace_bytes(int64_t N, int Fo, int G);
+/* colsum (nullable, [Fo + 2G]) receives the column sums of d pre = the bias gradients (needs workspace) */
 GNNML3_API int gnnml3_ml3_act_bwd(const float* pre, int64_t ldp, const float* gy, int64_t ldy, int64_t N, int Fo, int G,
-                       float* gpre, int64_t ldg, float* gate_out, int64_t ldgate, void* stream);
+                       float* gpre, int64_t ldg, float* gate_out, int64_t ldgate, float* colsum,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Readout: PyG global_add_pool (mean = 0) / global_mean_pool (mean = 1) over contiguous node ranges
