@@ -32,6 +32,9 @@ SIGNATURES = {
     "gnnml3_gemm_nn": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _i, _p]),
     "gnnml3_gemm_tn_workspace_bytes": (_sz, [_i64, _i, _i]),
     "gnnml3_gemm_tn": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i, _i, _i, _p, _sz, _p]),
+    "gnnml3_gemm_nn_tc_supported": (_i, [_i64, _i, _i]),
+    "gnnml3_gemm_nn_tc_workspace_bytes": (_sz, [_i, _i]),
+    "gnnml3_gemm_nn_tc": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _i, _p, _sz, _p]),
     "gnnml3_colsum_workspace_bytes": (_sz, [_i64, _i]),
     "gnnml3_colsum": (_i, [_p, _i64, _i64, _i, _p, _p, _sz, _p]),
     "gnnml3_edge_mlp_supported": (_i, [_i, _i]),

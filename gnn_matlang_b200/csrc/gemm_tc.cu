@@ -1,0 +1,403 @@
+// Blackwell-native tall-skinny GEMM:  C[M, Nc] = A[M, Kc] * B[Kc, Nc] (+ bias) (+ ReLU)  on the 5th-generation
+// tensor cores (tcgen05.mma kind::tf32, accumulators in tensor memory), FP32-grade through the 3xTF32 split.
+//
+// Used for the SpectConv projection sum_k P_k(x) W_k as ONE contraction over K*Fi (reference libs/spect_conv.py:80,
+// :93-94) and for the dx / dH contractions of its backward.  M (nodes) is huge, Nc and Kc are small, so the kernel
+// streams A from HBM exactly once and everything else stays on chip.
+//
+// Persistent, warp-specialised CTA (one per SM):
+//   warps 0-3  producers : 128-bit global loads of the A tile [128 x 32], split a = hi + lo (hi = RN-to-TF32), stored
+//                          as two planes straight into the UMMA canonical K-major SWIZZLE_128B layout; the (tiny,
+//                          host-pre-split, transposed) weight planes Bt_hi / Bt_lo are copied the same way.
+//   warp  4    MMA issuer: one elected lane issues, per 32-wide k-block, 4 x 3 tcgen05.mma (lo*hi + hi*lo + hi*hi)
+//                          into a TMEM accumulator; tcgen05.commit releases the smem stage / publishes the chunk.
+//   warps 5-8  epilogue  : tcgen05.ld the accumulator chunk (32 lanes x BN columns per warp), fold it into FP32
+//                          registers with round-to-nearest adds (the tensor core's own accumulate truncates, which
+//                          would bias long contractions), finally bias / ReLU and 128-bit row stores.
+// Two TMEM accumulator buffers ping-pong so the MMAs of chunk i+1 overlap the drain of chunk i; a 4-stage mbarrier
+// ring decouples the producers from the tensor core.
+#include "common.cuh"
+
+namespace gnnml3 {
+
+constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 4;
+constexpr int TC_PRODUCERS = 128, TC_EPILOGUE = 128;
+constexpr int TC_THREADS = TC_PRODUCERS + 32 + TC_EPILOGUE;   // 288
+constexpr int TC_A_BYTES = TC_BM * 128;                       // one [128 x 32] FP32 plane
+
+template <int BN>
+struct TCCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256));
+    static constexpr size_t SMEM = (size_t)TC_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, FP32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive FP32 columns of tensor memory -> 32 registers per thread (lane i <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor of a K-major tile whose rows are 128 bytes (32 FP32) in the SWIZZLE_128B canonical
+// layout: 8-row groups of 1024 bytes (stride-byte-offset), 16-byte chunks XOR-swizzled with the row index.
+// Fields (cute/arch/mma_sm100_desc.hpp semantics): [0,14) start>>4, [16,30) LBO>>4 (=1 for swizzled K-major),
+// [32,46) SBO>>4, [46,48) version = 1 (Blackwell), [61,64) layout type (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc_tf32() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------- weight planes
+// Bt_hi / Bt_lo [Npad][Kpad]: transposed (K-major), zero padded, pre-split weights.  Tiny (<= 256 x 2560).
+__global__ void k_prep_weights_tc(const float* __restrict__ B, int64_t ldb, int Kc, int Nc, int Kpad, int Npad,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+    const int total = Npad * Kpad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i / Kpad, k = i % Kpad;
+        const float v = (n < Nc && k < Kc) ? __ldg(B + (int64_t)k * ldb + n) : 0.f;
+        const float h = tf32_rn(v);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- the GEMM
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_nn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt_hi, const float* __restrict__ Bt_lo,
+             int Kpad, const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int Nc, int Kc,
+             int epi, int chunk_kb, int n_mtiles) {
+    using Cfg = TCCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES]  producers -> MMA
+    uint64_t* empty = bars + TC_STAGES;          // [STAGES]  MMA (tcgen05.commit) -> producers
+    uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]       MMA -> epilogue
+    uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * BN;
+    const int nkb = (Kc + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full + s, TC_PRODUCERS);
+            mbar_init(empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull + b, 1);
+            mbar_init(tempty + b, TC_EPILOGUE);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =================================================================== producers
+        const int tid = threadIdx.x;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
+            const int64_t m0 = (int64_t)tile * TC_BM;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (it / TC_STAGES) & 1;
+                // global loads first (registers), so their latency overlaps the wait for a free stage
+                float4 av[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int q = tid + TC_PRODUCERS * j;
+                    const int r = q >> 3, c = q & 7;
+                    const int64_t row = m0 + r;
+                    const int col = kb * TC_BK + c * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < M) {
+                        const float* p = A + row * lda + col;
+                        if (col + 3 < Kc) {
+                            v = ldg4(p);
+                        } else {
+                            if (col < Kc) v.x = __ldg(p);
+                            if (col + 1 < Kc) v.y = __ldg(p + 1);
+                            if (col + 2 < Kc) v.z = __ldg(p + 2);
+                        }
+                    }
+                    av[j] = v;
+                }
+                constexpr int BCH = (BN * 8 + TC_PRODUCERS - 1) / TC_PRODUCERS;
+                float4 bh[BCH], bl[BCH];
+#pragma unroll
+                for (int j = 0; j < BCH; ++j) {
+                    const int q = tid + TC_PRODUCERS * j;
+                    if (q < BN * 8) {
+                        const int n = q >> 3, c = q & 7;
+                        const int64_t off = (int64_t)(n0 + n) * Kpad + kb * TC_BK + c * 4;
+                        bh[j] = ldg4(Bt_hi + off);
+                        bl[j] = ldg4(Bt_lo + off);
+                    }
+                }
+                mbar_wait(empty + s, ph ^ 1);
+                uint8_t* st = smem + (size_t)s * Cfg::STAGE_BYTES;
+                uint8_t* a_hi = st;
+                uint8_t* a_lo = st + TC_A_BYTES;
+                uint8_t* b_hi = st + 2 * TC_A_BYTES;
+                uint8_t* b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int q = tid + TC_PRODUCERS * j;
+                    const int r = q >> 3, c = q & 7;
+                    const int off = r * 128 + ((c ^ (r & 7)) << 4);
+                    const float4 v = av[j];
+                    float4 h, l;
+                    h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    *reinterpret_cast<float4*>(a_hi + off) = h;
+                    *reinterpret_cast<float4*>(a_lo + off) = l;
+                }
+#pragma unroll
+                for (int j = 0; j < BCH; ++j) {
+                    const int q = tid + TC_PRODUCERS * j;
+                    if (q < BN * 8) {
+                        const int n = q >> 3, c = q & 7;
+                        const int off = n * 128 + ((c ^ (n & 7)) << 4);
+                        *reinterpret_cast<float4*>(b_hi + off) = bh[j];
+                        *reinterpret_cast<float4*>(b_lo + off) = bl[j];
+                    }
+                }
+                fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(full + s);
+            }
+        }
+    } else if (warp == 4) {
+        // =================================================================== MMA issuer (one lane)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32<BN>();
+            uint32_t it = 0, cc = 0;
+            for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t buf = cc & 1;
+                    const bool chunk_start = (kb % chunk_kb) == 0;
+                    if (chunk_start) {
+                        mbar_wait(tempty + buf, ((cc >> 1) & 1) ^ 1);    // epilogue has drained this accumulator
+                        tc_fence_after();
+                    }
+                    const int s = it % TC_STAGES;
+                    mbar_wait(full + s, (it / TC_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
+                    const uint64_t da_hi = make_kmajor_sw128_desc(sa);
+                    const uint64_t da_lo = make_kmajor_sw128_desc(sa + TC_A_BYTES);
+                    const uint64_t db_hi = make_kmajor_sw128_desc(sa + 2 * TC_A_BYTES);
+                    const uint64_t db_lo = make_kmajor_sw128_desc(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
+                    const uint32_t d = tmem_base + buf * BN;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 8 TF32 = 32 bytes along K inside the swizzled row
+                        umma_tf32(d, da_lo + adv, db_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                        umma_tf32(d, da_hi + adv, db_lo + adv, idesc, 1u);
+                        umma_tf32(d, da_hi + adv, db_hi + adv, idesc, 1u);
+                    }
+                    umma_commit(empty + s);                                    // stage reusable once these MMAs retire
+                    if ((kb % chunk_kb) == chunk_kb - 1 || kb == nkb - 1) {
+                        umma_commit(tfull + buf);                              // chunk complete -> epilogue
+                        ++cc;
+                    }
+                }
+            }
+        }
+    } else {
+        // =================================================================== epilogue
+        const int quarter = warp & 3;                       // TMEM lanes this warp may touch: [32*quarter, +32)
+        const int nchunks = (nkb + chunk_kb - 1) / chunk_kb;
+        uint32_t cc = 0;
+        for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
+            const int64_t row = (int64_t)tile * TC_BM + quarter * 32 + lane;
+            float acc[BN];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+            for (int ch = 0; ch < nchunks; ++ch, ++cc) {
+                const uint32_t buf = cc & 1;
+                mbar_wait(tfull + buf, (cc >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
+#pragma unroll
+                for (int j0 = 0; j0 < BN; j0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + j0, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[j0 + i] += v[i];
+                }
+                tc_fence_before();
+                mbar_arrive(tempty + buf);
+            }
+            if (row < M) {
+                float* dst = C + row * ldc + n0;
+                const bool vec = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (n0 % 4 == 0);
+#pragma unroll
+                for (int j = 0; j < BN; j += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float t = acc[j + i];
+                        if (bias && n0 + j + i < Nc) t += __ldg(bias + n0 + j + i);
+                        if (epi == GNNML3_EPI_RELU) t = fmaxf(t, 0.f);
+                        o[i] = t;
+                    }
+                    if (vec && n0 + j + 3 < Nc) {
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (n0 + j + i < Nc) dst[j + i] = o[i];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+}  // namespace gnnml3
+
+using namespace gnnml3;
+
+static inline int tc_bn_for(int Nc) { return Nc <= 32 ? 32 : 64; }
+
+extern "C" int gnnml3_gemm_nn_tc_supported(int64_t lda, int Nc, int Kc) {
+    return (lda % 4 == 0 && Nc >= 1 && Kc >= 1 && Nc <= 4096 && Kc <= 8192) ? 1 : 0;
+}
+
+extern "C" size_t gnnml3_gemm_nn_tc_workspace_bytes(int Nc, int Kc) {
+    const int BN = tc_bn_for(Nc);
+    const size_t Npad = (size_t)cdiv(Nc, BN) * BN, Kpad = (size_t)cdiv(Kc, TC_BK) * TC_BK;
+    return align_up(2 * Npad * Kpad * sizeof(float), 256);
+}
+
+template <int BN>
+static int launch_tc(const float* A, int64_t lda, const float* hi, const float* lo, int Kpad, const float* bias, float* C,
+                     int64_t ldc, int64_t M, int Nc, int Kc, int epi, int chunk_kb, cudaStream_t st) {
+    using Cfg = TCCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_nn_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int n_mtiles = cdiv(M, TC_BM);
+    const int gy = cdiv(Nc, BN);
+    int gx = kNumSMs / gy;
+    if (gx < 1) gx = 1;
+    if (gx > n_mtiles) gx = n_mtiles;
+    k_gemm_nn_tc<BN><<<dim3(gx, gy), TC_THREADS, Cfg::SMEM, st>>>(A, lda, hi, lo, Kpad, bias, C, ldc, M, Nc, Kc, epi, chunk_kb,
+                                                                  n_mtiles);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+extern "C" int gnnml3_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                                 int64_t ldc, int64_t M, int Nc, int Kc, int epilogue, int chunk_kblocks, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+    GNNML3_REQUIRE(M > 0 && Nc > 0 && Kc > 0, "gemm_nn_tc: bad shape");
+    GNNML3_REQUIRE(A && B && C && workspace, "gemm_nn_tc: NULL pointer");
+    GNNML3_REQUIRE(lda >= Kc && ldb >= Nc && ldc >= Nc, "gemm_nn_tc: leading dimensions too small");
+    GNNML3_REQUIRE(gnnml3_gemm_nn_tc_supported(lda, Nc, Kc) && (uintptr_t)A % 16 == 0,
+                   "gemm_nn_tc: A rows must be 16-byte aligned (lda %% 4 == 0)");
+    GNNML3_REQUIRE(epilogue == GNNML3_EPI_NONE || epilogue == GNNML3_EPI_RELU, "gemm_nn_tc: unknown epilogue");
+    GNNML3_REQUIRE(cdiv(M, TC_BM) < (1ll << 31), "gemm_nn_tc: M too large");
+    if (workspace_bytes < gnnml3_gemm_nn_tc_workspace_bytes(Nc, Kc))
+        return set_err(GNNML3_ERR_WORKSPACE, "gemm_nn_tc: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int BN = tc_bn_for(Nc);
+    const int Npad = cdiv(Nc, BN) * BN, Kpad = cdiv(Kc, TC_BK) * TC_BK;
+    float* hi = (float*)workspace;
+    float* lo = hi + (size_t)Npad * Kpad;
+    k_prep_weights_tc<<<cdiv((int64_t)Npad * Kpad, 256) > 592 ? 592 : cdiv((int64_t)Npad * Kpad, 256), 256, 0, st>>>(
+        B, ldb, Kc, Nc, Kpad, Npad, hi, lo);
+    GNNML3_LAUNCH_CHECK();
+    const int chunk = chunk_kblocks > 0 ? chunk_kblocks : 2;
+    if (BN == 32) return launch_tc<32>(A, lda, hi, lo, Kpad, bias, C, ldc, M, Nc, Kc, epilogue, chunk, st);
+    return launch_tc<64>(A, lda, hi, lo, Kpad, bias, C, ldc, M, Nc, Kc, epilogue, chunk, st);
+}

@@ -3,6 +3,8 @@
 PyTorch is used here only for device memory (torch.empty on the input's device) and for the current
 stream; all arithmetic happens inside libgnnml3_b200.so.  Every wrapper refuses CPU tensors.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -124,8 +126,36 @@ def sddmm_k(rowptr, col, eperm, x, g, K, E):
     return dea
 
 
+USE_TCGEN05 = os.environ.get("GNNML3_NO_TCGEN05", "0") != "1"
+TC_MIN_ROWS = 1024          # below this the persistent tcgen05 kernel cannot fill the machine; use the mma.sync path
+
+
+def gemm_nn_tc(A, B, bias=None, epilogue=_lib.EPI_NONE, out=None, chunk_kblocks=0):
+    """C = A @ B (+ bias) (+ relu) on tcgen05 / TMEM (3xTF32, FP32-grade).  A rows must be 16-byte aligned."""
+    lib = _lib.load()
+    A = _rows(A, "A")
+    B = _f32c(B, "B")
+    M, Kc = A.shape
+    Nc = B.size(1)
+    if B.size(0) != Kc:
+        raise RuntimeError("gemm_nn_tc: inner dimensions differ (%d vs %d)" % (Kc, B.size(0)))
+    if out is None:
+        out = torch.empty(M, Nc, dtype=torch.float32, device=A.device)
+    if M == 0:
+        return out
+    if bias is not None:
+        bias = _f32c(bias, "bias")
+    ws = _ws(A.device, lib.gnnml3_gemm_nn_tc_workspace_bytes(Nc, Kc), tag="tc")
+    with torch.cuda.device(A.device):
+        _lib.check(lib.gnnml3_gemm_nn_tc(_lib.ptr(A), _ld(A), _lib.ptr(B), _ld(B), _lib.ptr(bias), _lib.ptr(out), _ld(out),
+                                         M, Nc, Kc, epilogue, chunk_kblocks, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "gnnml3_gemm_nn_tc")
+    return out
+
+
 def gemm_nn(A, B, bias=None, precision=_lib.PREC_3XTF32, epilogue=_lib.EPI_NONE, out=None):
-    """C = A @ B (+ bias) (+ relu) on the tensor cores; A [M,Kc], B [Kc,Nc]."""
+    """C = A @ B (+ bias) (+ relu) on the tensor cores; A [M,Kc], B [Kc,Nc].  FP32-grade (3xTF32) requests with
+    16-byte aligned rows run on tcgen05/TMEM; everything else on the mma.sync kernel."""
     lib = _lib.load()
     A = _rows(A, "A")
     B = _f32c(B, "B")
@@ -133,6 +163,9 @@ def gemm_nn(A, B, bias=None, precision=_lib.PREC_3XTF32, epilogue=_lib.EPI_NONE,
     Nc = B.size(1)
     if B.size(0) != Kc:
         raise RuntimeError("gemm_nn: inner dimensions differ (%d vs %d)" % (Kc, B.size(0)))
+    if (USE_TCGEN05 and precision == _lib.PREC_3XTF32 and M >= TC_MIN_ROWS and _ld(A) % 4 == 0 and A.data_ptr() % 16 == 0
+            and lib.gnnml3_gemm_nn_tc_supported(_ld(A), Nc, Kc)):
+        return gemm_nn_tc(A, B, bias, epilogue, out)
     if out is None:
         out = torch.empty(M, Nc, dtype=torch.float32, device=A.device)
     if M == 0:
@@ -232,7 +265,10 @@ def ml3_act_bwd(pre, gy, Fo, G, gate_out=None):
     lib = _lib.load()
     gy = _f32c(gy, "gy")
     N = pre.size(0)
-    gpre = torch.empty(N, Fo + 2 * G, dtype=torch.float32, device=pre.device)
+    # rows padded to a multiple of 4 floats: the column-block views of gpre then have 16-byte aligned rows and
+    # qualify for 128-bit loads / the tcgen05 GEMM
+    ld4 = (Fo + 2 * G + 3) // 4 * 4
+    gpre = torch.empty(N, ld4, dtype=torch.float32, device=pre.device)[:, :Fo + 2 * G]
     csum = torch.empty(Fo + 2 * G, dtype=torch.float32, device=pre.device)
     ws = _ws(pre.device, lib.gnnml3_ml3_act_bwd_workspace_bytes(N, Fo, G))
     with torch.cuda.device(pre.device):
@@ -301,6 +337,6 @@ def _instrument(name, fn):
     return wrapped
 
 
-for _n in ("csr_build", "gather_rows", "scatter_rows", "spmm_k", "sddmm_k", "gemm_nn", "gemm_tn", "colsum", "edge_mlp_fwd",
+for _n in ("csr_build", "gather_rows", "scatter_rows", "spmm_k", "sddmm_k", "gemm_nn_tc", "gemm_nn", "gemm_tn", "colsum", "edge_mlp_fwd",
            "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "segment_pool_fwd", "segment_pool_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

@@ -158,6 +158,18 @@ GNNML3_API int gnnml3_spectral_design(const int64_t* edge_index, int64_t Etot, c
                            double vmax, int nmax, const int64_t* out_ptr, int global_ids, int64_t* edge_index2,
                            int64_t E2, float* edge_attr2, float* lmax, float* degree, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Blackwell tensor-core path of gemm_nn: tcgen05.mma kind::tf32 with TMEM accumulators, 3xTF32 split,
+ * persistent warp-specialised CTAs (csrc/gemm_tc.cu).  Same contract as gnnml3_gemm_nn (FP32-grade result);
+ * requires 16-byte aligned rows of A (lda % 4 == 0).  chunk_kblocks = number of 32-wide k-blocks accumulated
+ * inside the tensor core before the partial sum is folded into FP32 registers (0 = default 2).
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_gemm_nn_tc_supported(int64_t lda, int Nc, int Kc);
+GNNML3_API size_t gnnml3_gemm_nn_tc_workspace_bytes(int Nc, int Kc);
+GNNML3_API int gnnml3_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                      int64_t ldc, int64_t M, int Nc, int Kc, int epilogue, int chunk_kblocks, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
