@@ -6,31 +6,38 @@
 // streams A from HBM exactly once and everything else stays on chip.
 //
 // Persistent, warp-specialised CTA (one per SM):
-//   warps 0-3  producers : 128-bit global loads of the A tile [128 x 32], split a = hi + lo (hi = RN-to-TF32), stored
-//                          as two planes straight into the UMMA canonical K-major SWIZZLE_128B layout; the (tiny,
-//                          host-pre-split, transposed) weight planes Bt_hi / Bt_lo are copied the same way.
-//   warp  4    MMA issuer: one elected lane issues, per 32-wide k-block, 4 x 3 tcgen05.mma (lo*hi + hi*lo + hi*hi)
+//   warp  0    TMA producer: one lane issues cp.async.bulk.tensor loads of the raw A tile [128 x 32 FP32] and of the
+//                          (tiny, host-pre-split, transposed) weight planes Bt_hi / Bt_lo straight into the UMMA
+//                          canonical K-major SWIZZLE_128B layout (zero fill outside the matrix), STAGES deep.
+//   warps 1-4  splitters : a = hi + lo with hi = the TF32 truncation the tensor core itself applies to the raw plane,
+//                          so only lo = a - trunc(a) has to be materialised: one LDS.128 / STS.128 pair per 16 bytes at
+//                          the SAME (swizzled) offset -- no index arithmetic, no second copy of hi.
+//   warp  5    MMA issuer: one elected lane issues, per 32-wide k-block, 4 x 3 tcgen05.mma (lo*hi + hi*lo + hi*hi)
 //                          into a TMEM accumulator; tcgen05.commit releases the smem stage / publishes the chunk.
-//   warps 5-8  epilogue  : tcgen05.ld the accumulator chunk (32 lanes x BN columns per warp), fold it into FP32
+//   warps 6-9  epilogue  : tcgen05.ld the accumulator chunk (32 lanes x BN columns per warp), fold it into FP32
 //                          registers with round-to-nearest adds (the tensor core's own accumulate truncates, which
 //                          would bias long contractions), finally bias / ReLU and 128-bit row stores.
-// Two TMEM accumulator buffers ping-pong so the MMAs of chunk i+1 overlap the drain of chunk i; a 4-stage mbarrier
-// ring decouples the producers from the tensor core.
+// 256 TMEM columns hold 4-8 accumulator buffers, so the MMAs run up to a tile ahead of the drain; a 4-stage mbarrier
+// ring (raw landed -> split done -> MMAs retired) decouples TMA, splitters and the tensor core.
 #include "common.cuh"
+
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
 
 namespace gnnml3 {
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 4;
-constexpr int TC_PRODUCERS = 128, TC_EPILOGUE = 128;
-constexpr int TC_THREADS = TC_PRODUCERS + 32 + TC_EPILOGUE;   // 288
+constexpr int TC_SPLITTERS = 128, TC_EPILOGUE = 128;
+constexpr int TC_THREADS = 32 + TC_SPLITTERS + 32 + TC_EPILOGUE;   // 320: TMA | splitters | MMA | epilogue
 constexpr int TC_A_BYTES = TC_BM * 128;                       // one [128 x 32] FP32 plane
 
 template <int BN>
 struct TCCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256));
-    static constexpr size_t SMEM = (size_t)TC_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int NBUF = 256 / BN;          // TMEM accumulator buffers (8 x 32 or 4 x 64 columns): the MMAs may run
+    static constexpr int TMEM_COLS = 256;          // a whole tile ahead while the epilogue is still storing the previous one
+    static constexpr uint32_t TX_BYTES = TC_A_BYTES + 2 * B_BYTES;    // bytes TMA delivers per stage
+    static constexpr size_t SMEM = (size_t)TC_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -41,6 +48,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load (box given by the tensor map) -> shared memory, completion reported to an mbarrier in bytes
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
@@ -142,18 +160,20 @@ __global__ void k_prep_weights_tc(const float* __restrict__ B, int64_t ldb, int 
 // ---------------------------------------------------------------------------------------------- the GEMM
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_gemm_nn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt_hi, const float* __restrict__ Bt_lo,
-             int Kpad, const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int Nc, int Kc,
-             int epi, int chunk_kb, int n_mtiles) {
+k_gemm_nn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
+             const __grid_constant__ CUtensorMap mapBlo, const float* __restrict__ bias, float* __restrict__ C, int64_t ldc,
+             int64_t M, int Nc, int Kc, int epi, int chunk_kb, int n_mtiles) {
     using Cfg = TCCfg<BN>;
+    constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;                       // [STAGES]  producers -> MMA
-    uint64_t* empty = bars + TC_STAGES;          // [STAGES]  MMA (tcgen05.commit) -> producers
-    uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]       MMA -> epilogue
-    uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]       epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    uint64_t* raw_full = bars;                         // [STAGES]  TMA bytes landed              -> splitters
+    uint64_t* full = bars + TC_STAGES;                 // [STAGES]  lo plane written              -> MMA
+    uint64_t* empty = bars + 2 * TC_STAGES;            // [STAGES]  MMAs retired (tcgen05.commit) -> TMA
+    uint64_t* tfull = bars + 3 * TC_STAGES;            // [NBUF]    accumulator chunk complete    -> epilogue
+    uint64_t* tempty = bars + 3 * TC_STAGES + NBUF;    // [NBUF]    accumulator drained           -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 2 * NBUF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
@@ -161,106 +181,79 @@ k_gemm_nn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(full + s, TC_PRODUCERS);
+            mbar_init(raw_full + s, 1);
+            mbar_init(full + s, TC_SPLITTERS / 32);
             mbar_init(empty + s, 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             mbar_init(tfull + b, 1);
-            mbar_init(tempty + b, TC_EPILOGUE);
+            mbar_init(tempty + b, TC_EPILOGUE / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
     }
-    if (warp == 4) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // =================================================================== producers
-        const int tid = threadIdx.x;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
-            const int64_t m0 = (int64_t)tile * TC_BM;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (it / TC_STAGES) & 1;
-                // global loads first (registers), so their latency overlaps the wait for a free stage
-                float4 av[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int q = tid + TC_PRODUCERS * j;
-                    const int r = q >> 3, c = q & 7;
-                    const int64_t row = m0 + r;
-                    const int col = kb * TC_BK + c * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < M) {
-                        const float* p = A + row * lda + col;
-                        if (col + 3 < Kc) {
-                            v = ldg4(p);
-                        } else {
-                            if (col < Kc) v.x = __ldg(p);
-                            if (col + 1 < Kc) v.y = __ldg(p + 1);
-                            if (col + 2 < Kc) v.z = __ldg(p + 2);
-                        }
-                    }
-                    av[j] = v;
+    if (warp == 0) {
+        // =================================================================== TMA producer (one lane)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
+                const int m0 = tile * TC_BM;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    mbar_wait(empty + s, ((it / TC_STAGES) & 1) ^ 1);
+                    uint8_t* st = smem + (size_t)s * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(raw_full + s, Cfg::TX_BYTES);
+                    tma_load_2d(st, &mapA, raw_full + s, kb * TC_BK, m0);                                  // raw A (= hi)
+                    tma_load_2d(st + 2 * TC_A_BYTES, &mapBhi, raw_full + s, kb * TC_BK, n0);               // Bt_hi
+                    tma_load_2d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &mapBlo, raw_full + s, kb * TC_BK, n0); // Bt_lo
                 }
-                constexpr int BCH = (BN * 8 + TC_PRODUCERS - 1) / TC_PRODUCERS;
-                float4 bh[BCH], bl[BCH];
-#pragma unroll
-                for (int j = 0; j < BCH; ++j) {
-                    const int q = tid + TC_PRODUCERS * j;
-                    if (q < BN * 8) {
-                        const int n = q >> 3, c = q & 7;
-                        const int64_t off = (int64_t)(n0 + n) * Kpad + kb * TC_BK + c * 4;
-                        bh[j] = ldg4(Bt_hi + off);
-                        bl[j] = ldg4(Bt_lo + off);
-                    }
-                }
-                mbar_wait(empty + s, ph ^ 1);
-                uint8_t* st = smem + (size_t)s * Cfg::STAGE_BYTES;
-                uint8_t* a_hi = st;
-                uint8_t* a_lo = st + TC_A_BYTES;
-                uint8_t* b_hi = st + 2 * TC_A_BYTES;
-                uint8_t* b_lo = b_hi + Cfg::B_BYTES;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int q = tid + TC_PRODUCERS * j;
-                    const int r = q >> 3, c = q & 7;
-                    const int off = r * 128 + ((c ^ (r & 7)) << 4);
-                    const float4 v = av[j];
-                    float4 h, l;
-                    h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
-                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                    *reinterpret_cast<float4*>(a_hi + off) = h;
-                    *reinterpret_cast<float4*>(a_lo + off) = l;
-                }
-#pragma unroll
-                for (int j = 0; j < BCH; ++j) {
-                    const int q = tid + TC_PRODUCERS * j;
-                    if (q < BN * 8) {
-                        const int n = q >> 3, c = q & 7;
-                        const int off = n * 128 + ((c ^ (n & 7)) << 4);
-                        *reinterpret_cast<float4*>(b_hi + off) = bh[j];
-                        *reinterpret_cast<float4*>(b_lo + off) = bl[j];
-                    }
-                }
-                fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
-                mbar_arrive(full + s);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp <= 4) {
+        // =================================================================== splitters: lo = a - trunc_tf32(a)
+        const int tid = threadIdx.x - 32;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                mbar_wait(raw_full + s, (it / TC_STAGES) & 1);
+                const uint8_t* a_raw = smem + (size_t)s * Cfg::STAGE_BYTES;
+                uint8_t* a_lo = smem + (size_t)s * Cfg::STAGE_BYTES + TC_A_BYTES;
+#pragma unroll
+                for (int j = 0; j < TC_A_BYTES / 16 / TC_SPLITTERS; ++j) {
+                    const int off = (tid + TC_SPLITTERS * j) * 16;
+                    const float4 v = *reinterpret_cast<const float4*>(a_raw + off);
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    *reinterpret_cast<float4*>(a_lo + off) = l;
+                }
+                fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + s);
+            }
+        }
+    } else if (warp == 5) {
         // =================================================================== MMA issuer (one lane)
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32<BN>();
             uint32_t it = 0, cc = 0;
             for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t buf = cc & 1;
+                    const uint32_t buf = cc % NBUF;
                     const bool chunk_start = (kb % chunk_kb) == 0;
                     if (chunk_start) {
-                        mbar_wait(tempty + buf, ((cc >> 1) & 1) ^ 1);    // epilogue has drained this accumulator
+                        mbar_wait(tempty + buf, ((cc / NBUF) & 1) ^ 1);    // epilogue has drained this accumulator
                         tc_fence_after();
                     }
                     const int s = it % TC_STAGES;
@@ -298,8 +291,8 @@ k_gemm_nn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
 #pragma unroll
             for (int j = 0; j < BN; ++j) acc[j] = 0.f;
             for (int ch = 0; ch < nchunks; ++ch, ++cc) {
-                const uint32_t buf = cc & 1;
-                mbar_wait(tfull + buf, (cc >> 1) & 1);
+                const uint32_t buf = cc % NBUF;
+                mbar_wait(tfull + buf, (cc / NBUF) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
 #pragma unroll
@@ -310,7 +303,8 @@ k_gemm_nn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
                     for (int i = 0; i < 32; ++i) acc[j0 + i] += v[i];
                 }
                 tc_fence_before();
-                mbar_arrive(tempty + buf);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + buf);
             }
             if (row < M) {
                 float* dst = C + row * ldc + n0;
@@ -338,7 +332,7 @@ k_gemm_nn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 }  // namespace gnnml3
@@ -357,21 +351,56 @@ extern "C" size_t gnnml3_gemm_nn_tc_workspace_bytes(int Nc, int Kc) {
     return align_up(2 * Npad * Kpad * sizeof(float), 256);
 }
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encoder() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// row-major FP32 matrix [rows, cols] (row stride ld floats) -> 2-D tensor map with a [box_rows x 32] box, 128B swizzle
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_encodeTiled enc = get_encoder();
+    if (!enc) return set_err(GNNML3_ERR_CUDA, "gemm_nn_tc: cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(GNNML3_ERR_CUDA, "gemm_nn_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return GNNML3_OK;
+}
+
 template <int BN>
-static int launch_tc(const float* A, int64_t lda, const float* hi, const float* lo, int Kpad, const float* bias, float* C,
-                     int64_t ldc, int64_t M, int Nc, int Kc, int epi, int chunk_kb, cudaStream_t st) {
+static int launch_tc(const float* A, int64_t lda, const float* hi, const float* lo, int Kpad, int Npad, const float* bias,
+                     float* C, int64_t ldc, int64_t M, int Nc, int Kc, int epi, int chunk_kb, cudaStream_t st) {
     using Cfg = TCCfg<BN>;
     static bool configured = false;
     if (!configured) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_nn_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
+    CUtensorMap mapA, mapBhi, mapBlo;
+    int rc;
+    if ((rc = make_map(&mapA, A, M, Kc, lda, TC_BM))) return rc;
+    if ((rc = make_map(&mapBhi, hi, Npad, Kpad, Kpad, BN))) return rc;
+    if ((rc = make_map(&mapBlo, lo, Npad, Kpad, Kpad, BN))) return rc;
     const int n_mtiles = cdiv(M, TC_BM);
     const int gy = cdiv(Nc, BN);
     int gx = kNumSMs / gy;
     if (gx < 1) gx = 1;
     if (gx > n_mtiles) gx = n_mtiles;
-    k_gemm_nn_tc<BN><<<dim3(gx, gy), TC_THREADS, Cfg::SMEM, st>>>(A, lda, hi, lo, Kpad, bias, C, ldc, M, Nc, Kc, epi, chunk_kb,
+    k_gemm_nn_tc<BN><<<dim3(gx, gy), TC_THREADS, Cfg::SMEM, st>>>(mapA, mapBhi, mapBlo, bias, C, ldc, M, Nc, Kc, epi, chunk_kb,
                                                                   n_mtiles);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
@@ -386,7 +415,7 @@ extern "C" int gnnml3_gemm_nn_tc(const float* A, int64_t lda, const float* B, in
     GNNML3_REQUIRE(gnnml3_gemm_nn_tc_supported(lda, Nc, Kc) && (uintptr_t)A % 16 == 0,
                    "gemm_nn_tc: A rows must be 16-byte aligned (lda %% 4 == 0)");
     GNNML3_REQUIRE(epilogue == GNNML3_EPI_NONE || epilogue == GNNML3_EPI_RELU, "gemm_nn_tc: unknown epilogue");
-    GNNML3_REQUIRE(cdiv(M, TC_BM) < (1ll << 31), "gemm_nn_tc: M too large");
+    GNNML3_REQUIRE(M < (1ll << 31) - TC_BM, "gemm_nn_tc: M too large");
     if (workspace_bytes < gnnml3_gemm_nn_tc_workspace_bytes(Nc, Kc))
         return set_err(GNNML3_ERR_WORKSPACE, "gemm_nn_tc: workspace too small");
     cudaStream_t st = (cudaStream_t)stream_;
@@ -397,7 +426,7 @@ extern "C" int gnnml3_gemm_nn_tc(const float* A, int64_t lda, const float* B, in
     k_prep_weights_tc<<<cdiv((int64_t)Npad * Kpad, 256) > 592 ? 592 : cdiv((int64_t)Npad * Kpad, 256), 256, 0, st>>>(
         B, ldb, Kc, Nc, Kpad, Npad, hi, lo);
     GNNML3_LAUNCH_CHECK();
-    const int chunk = chunk_kblocks > 0 ? chunk_kblocks : 2;
-    if (BN == 32) return launch_tc<32>(A, lda, hi, lo, Kpad, bias, C, ldc, M, Nc, Kc, epilogue, chunk, st);
-    return launch_tc<64>(A, lda, hi, lo, Kpad, bias, C, ldc, M, Nc, Kc, epilogue, chunk, st);
+    const int chunk = chunk_kblocks > 0 ? chunk_kblocks : 4;   // 4 k-blocks (48 MMAs) per TMEM chunk: rel. error ~1e-6
+    if (BN == 32) return launch_tc<32>(A, lda, hi, lo, Kpad, Npad, bias, C, ldc, M, Nc, Kc, epilogue, chunk, st);
+    return launch_tc<64>(A, lda, hi, lo, Kpad, Npad, bias, C, ldc, M, Nc, Kc, epilogue, chunk, st);
 }

@@ -162,7 +162,7 @@ GNNML3_API int gnnml3_spectral_design(const int64_t* edge_index, int64_t Etot, c
  * Blackwell tensor-core path of gemm_nn: tcgen05.mma kind::tf32 with TMEM accumulators, 3xTF32 split,
  * persistent warp-specialised CTAs (csrc/gemm_tc.cu).  Same contract as gnnml3_gemm_nn (FP32-grade result);
  * requires 16-byte aligned rows of A (lda % 4 == 0).  chunk_kblocks = number of 32-wide k-blocks accumulated
- * inside the tensor core before the partial sum is folded into FP32 registers (0 = default 2).
+ * inside the tensor core before the partial sum is folded into FP32 registers (0 = default 4).
  * --------------------------------------------------------------------------------------------------- */
 GNNML3_API int gnnml3_gemm_nn_tc_supported(int64_t lda, int Nc, int Kc);
 GNNML3_API size_t gnnml3_gemm_nn_tc_workspace_bytes(int Nc, int Kc);
