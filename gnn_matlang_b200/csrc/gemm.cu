@@ -223,35 +223,41 @@ k_gemm_nn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 }
 
 // ------------------------------------------------------------------------------------------------ gemm_tn
-constexpr int TN_BA = 64, TN_BB = 64, TN_BK = 32, TN_STAGES = 3, TN_THREADS = 128, TN_LD = 72;
-constexpr size_t tn_smem_bytes() { return sizeof(float) * TN_STAGES * TN_BK * TN_LD * 2; }
+constexpr int TN_BB = 64, TN_BK = 32, TN_STAGES = 3, TN_THREADS = 128, TN_LD = 72;
+template <int BA>
+constexpr size_t tn_smem_bytes() { return sizeof(float) * TN_STAGES * TN_BK * (BA + 8 + TN_LD); }
 
-template <bool VA, bool VB, bool X3>
+// BA = 64: 2 x 2 warps of 32 x 32;  BA = 32 (Ka <= 32, e.g. x^T G' with 32 input features): 1 x 4 warps of 32 x 16, so
+// no MMA is spent on padding rows of the A^T tile.
+template <int BA, bool VA, bool VB, bool X3>
 __global__ void __launch_bounds__(TN_THREADS)
 k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ P,
           int64_t M, int Ka, int Nb, int64_t rows_per_split) {
+    constexpr int LDA = BA + 8;
+    constexpr int WA = BA / 32, WB = 4 / WA;       // warp grid
+    constexpr int NTB = TN_BB / WB / 8;            // n-tiles per warp
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
-    float* Bs = smem + TN_STAGES * TN_BK * TN_LD;
+    float* Bs = smem + TN_STAGES * TN_BK * LDA;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wa = warp & 1, wb = warp >> 1;
-    const int a0 = blockIdx.x * TN_BA, b0 = blockIdx.y * TN_BB;
+    const int wa = warp % WA, wb = warp / WA;
+    const int a0 = blockIdx.x * BA, b0 = blockIdx.y * TN_BB;
     const int64_t mbeg = (int64_t)blockIdx.z * rows_per_split;
     const int64_t mend = min(M, mbeg + rows_per_split);
     const int nk = (int)((mend - mbeg + TN_BK - 1) / TN_BK);
 
-    float acc[2][4][4];
+    float acc[2][NTB][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NTB; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
 
     auto issue = [&](int kt) {
         const int st = kt % TN_STAGES;
-        load_tile<TN_BK, TN_BA, TN_LD, TN_THREADS, VA>(As + st * TN_BK * TN_LD, A, lda, mbeg + (int64_t)kt * TN_BK, a0, mend, Ka);
+        load_tile<TN_BK, BA, LDA, TN_THREADS, VA>(As + st * TN_BK * LDA, A, lda, mbeg + (int64_t)kt * TN_BK, a0, mend, Ka);
         load_tile<TN_BK, TN_BB, TN_LD, TN_THREADS, VB>(Bs + st * TN_BK * TN_LD, B, ldb, mbeg + (int64_t)kt * TN_BK, b0, mend, Nb);
     };
 #pragma unroll
@@ -264,13 +270,13 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
         __syncthreads();
         if (kt + TN_STAGES - 1 < nk) issue(kt + TN_STAGES - 1);
         cp_async_commit();
-        const float* as = As + (kt % TN_STAGES) * TN_BK * TN_LD + wa * 32;
-        const float* bs = Bs + (kt % TN_STAGES) * TN_BK * TN_LD + wb * 32;
-        float tacc[2][4][4];   // per-k-tile accumulators, see k_gemm_nn
+        const float* as = As + (kt % TN_STAGES) * TN_BK * LDA + wa * 32;
+        const float* bs = Bs + (kt % TN_STAGES) * TN_BK * TN_LD + wb * (TN_BB / WB);
+        float tacc[2][NTB][4];   // per-k-tile accumulators, see k_gemm_nn
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NTB; ++j)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) tacc[i][j][r] = 0.f;
 #pragma unroll
@@ -278,11 +284,11 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
             float af[2][4];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {  // A^T fragment: (row = A column, col = node)
-                const float* p = as + (kk * 8 + t) * TN_LD + i * 16 + g;
+                const float* p = as + (kk * 8 + t) * LDA + i * 16 + g;
                 af[i][0] = p[0];
                 af[i][1] = p[8];
-                af[i][2] = p[4 * TN_LD];
-                af[i][3] = p[4 * TN_LD + 8];
+                af[i][2] = p[4 * LDA];
+                af[i][3] = p[4 * LDA + 8];
             }
             uint32_t ah[2][4], al[2][4];
 #pragma unroll
@@ -295,7 +301,7 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NTB; ++j) {
                 const float* p = bs + (kk * 8 + t) * TN_LD + j * 8 + g;
                 const float bf[2] = {p[0], p[4 * TN_LD]};
                 uint32_t bh[2], bl[2];
@@ -318,7 +324,7 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NTB; ++j)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) acc[i][j][r] += tacc[i][j][r];
     }
@@ -327,11 +333,11 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NTB; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int ra = a0 + wa * 32 + i * 16 + g + (r >> 1) * 8;
-                const int cb = b0 + wb * 32 + j * 8 + 2 * t + (r & 1);
+                const int cb = b0 + wb * (TN_BB / WB) + j * 8 + 2 * t + (r & 1);
                 if (ra < Ka && cb < Nb) Pz[(int64_t)ra * Nb + cb] = acc[i][j][r];
             }
 }
@@ -355,8 +361,10 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
     }
 }
 
+static inline int tn_ba_for(int Ka) { return Ka <= 32 ? 32 : 64; }
+
 static void tn_plan(int64_t M, int Ka, int Nb, int* splits, int64_t* rows_per_split) {
-    const int tiles = cdiv(Ka, TN_BA) * cdiv(Nb, TN_BB);
+    const int tiles = cdiv(Ka, tn_ba_for(Ka)) * cdiv(Nb, TN_BB);
     int s = (4 * kNumSMs + tiles - 1) / tiles;
     int64_t maxs = (M + 4 * TN_BK - 1) / (4 * TN_BK);
     if (s > maxs) s = (int)maxs;
@@ -449,27 +457,27 @@ extern "C" size_t gnnml3_gemm_tn_workspace_bytes(int64_t M, int Ka, int Nb) {
     return align_up((size_t)splits * Ka * Nb * sizeof(float), 256);
 }
 
-template <bool VA, bool VB, bool X3>
+template <int BA, bool VA, bool VB, bool X3>
 static int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb,
                      int splits, int64_t rps, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn<VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem_bytes()));
+        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn<BA, VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem_bytes<BA>()));
         configured = true;
     }
-    dim3 grid(cdiv(Ka, TN_BA), cdiv(Nb, TN_BB), splits);
-    k_gemm_tn<VA, VB, X3><<<grid, TN_THREADS, tn_smem_bytes(), st>>>(A, lda, B, ldb, P, M, Ka, Nb, rps);
+    dim3 grid(cdiv(Ka, BA), cdiv(Nb, TN_BB), splits);
+    k_gemm_tn<BA, VA, VB, X3><<<grid, TN_THREADS, tn_smem_bytes<BA>(), st>>>(A, lda, B, ldb, P, M, Ka, Nb, rps);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
 
-template <bool X3>
+template <int BA, bool X3>
 static int launch_tn_v(bool va, bool vb, const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka,
                        int Nb, int splits, int64_t rps, cudaStream_t st) {
-    if (va && vb) return launch_tn<true, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
-    if (va) return launch_tn<true, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
-    if (vb) return launch_tn<false, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
-    return launch_tn<false, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (va && vb) return launch_tn<BA, true, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (va) return launch_tn<BA, true, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (vb) return launch_tn<BA, false, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    return launch_tn<BA, false, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
 }
 
 extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
@@ -489,8 +497,13 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
     const bool va = (lda % 4 == 0 || M == 1) && (uintptr_t)A % 16 == 0;
     const bool vb = (ldb % 4 == 0 || M == 1) && (uintptr_t)B % 16 == 0;
     float* P = (float*)workspace;
-    const int rc = precision == GNNML3_PREC_3XTF32 ? launch_tn_v<true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
-                                                   : launch_tn_v<false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    int rc;
+    if (tn_ba_for(Ka) == 32)
+        rc = precision == GNNML3_PREC_3XTF32 ? launch_tn_v<32, true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
+                                             : launch_tn_v<32, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    else
+        rc = precision == GNNML3_PREC_3XTF32 ? launch_tn_v<64, true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
+                                             : launch_tn_v<64, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
     if (rc) return rc;
     const int64_t n = (int64_t)Ka * Nb;
     k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, splits, n, Nb, C, ldc);

@@ -187,7 +187,8 @@ class _ML3LayerFn(torch.autograd.Function):
         else:
             ea2 = ea_s
         H = _aggregate(plan, ea2, x, K)
-        pre = torch.empty(N, Fo + 2 * G, dtype=torch.float32, device=x.device)
+        # rows padded to a multiple of 4 floats so that the GEMM epilogues can store 128-bit vectors
+        pre = torch.empty(N, (Fo + 2 * G + 3) // 4 * 4, dtype=torch.float32, device=x.device)[:, :Fo + 2 * G]
         if N > 0:
             ops.gemm_nn(H, wconv.view(K * Fi, Fo), bconv, precision=precision, out=pre[:, :Fo])
             if G > 0:
