@@ -28,7 +28,6 @@ SIGNATURES = {
     "gnnml3_gather_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
     "gnnml3_scatter_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
     "gnnml3_spmm_k": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p, _i64, _p]),
-    "gnnml3_spmm_set_mode": (None, [_i]),
     "gnnml3_sddmm_k": (_i, [_p, _p, _p, _p, _i64, _p, _i64, _i64, _i, _i, _p, _p]),
     "gnnml3_gemm_nn": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _i, _p]),
     "gnnml3_gemm_tn_workspace_bytes": (_sz, [_i64, _i, _i]),

@@ -133,136 +133,6 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ col, const int* _
     }
 }
 
-// Block-staged variant (the default for batches of small graphs).  A CTA owns SP_ROWS consecutive rows; because the
-// CSR is dst-sorted their edges form ONE contiguous range, so the CTA first streams that range's source indices and
-// K edge-weight channels into shared memory with fully coalesced, independent loads, together with a window of
-// source rows of x around its own rows (the sources of a batched disjoint graph are the neighbouring rows of the same
-// graph).  The per-row reduction then runs out of shared memory: no dependent index -> weight -> gather chains on
-// global-memory latency, which is what kept the direct kernel at ~40 % of the HBM roofline.  Sources outside the
-// window (large graphs) and CTAs whose edge range exceeds the staging buffer fall back to global loads.
-constexpr int SP_ROWS = 64;
-
-template <int K, int VEC, int CH>
-__global__ void __launch_bounds__(256)
-k_spmm_staged(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ eperm,
-              const float* __restrict__ ea, const float* __restrict__ x, int64_t ldx, int N, int F, int G, int Kstride,
-              float* __restrict__ out, int64_t ldo, int emax, int win) {
-    extern __shared__ __align__(16) unsigned char sp_smem[];
-    float* s_w = reinterpret_cast<float*>(sp_smem);                  // [emax][K]
-    float* s_x = s_w + (size_t)emax * K;                             // [(SP_ROWS + 2 win)][F]
-    int* s_col = reinterpret_cast<int*>(s_x + (size_t)(SP_ROWS + 2 * win) * F);   // [emax]
-    int* s_rp = s_col + emax;                                        // [SP_ROWS + 1]
-
-    const int tid = threadIdx.x;
-    const int r0 = blockIdx.x * SP_ROWS;
-    const int r1 = min(N, r0 + SP_ROWS);
-    const int nr = r1 - r0;
-    for (int i = tid; i <= nr; i += blockDim.x) s_rp[i] = __ldg(rowptr + r0 + i);
-    __syncthreads();
-    const int e0 = s_rp[0], ne = s_rp[nr] - e0;
-    const bool staged = ne <= emax;
-    const int w0 = max(0, r0 - win), w1 = min(N, r1 + win);
-    if (staged) {
-        for (int i = tid; i < ne; i += blockDim.x) s_col[i] = __ldg(col + e0 + i);
-        if (eperm == nullptr && Kstride == K) {                      // contiguous weights: plain coalesced copy
-            const float* src = ea + (int64_t)e0 * K;
-            for (int i = tid; i < ne * K; i += blockDim.x) s_w[i] = __ldg(src + i);
-        } else {
-            for (int i = tid; i < ne * K; i += blockDim.x) {
-                const int e = i / K, k = i - e * K;
-                const int64_t se = eperm ? (int64_t)__ldg(eperm + e0 + e) : (int64_t)(e0 + e);
-                s_w[i] = __ldg(ea + se * Kstride + k);
-            }
-        }
-    }
-    if (win > 0) {
-        const int nw = (w1 - w0) * F;
-        if constexpr (VEC == 4) {
-            for (int i = tid * 4; i < nw; i += blockDim.x * 4) {
-                const int r = i / F, c = i - r * F;
-                *reinterpret_cast<float4*>(s_x + i) = ldg4(x + (int64_t)(w0 + r) * ldx + c);
-            }
-        } else {
-            for (int i = tid; i < nw; i += blockDim.x) {
-                const int r = i / F, c = i - r * F;
-                s_x[i] = __ldg(x + (int64_t)(w0 + r) * ldx + c);
-            }
-        }
-    }
-    __syncthreads();
-
-    const int g = tid & (G - 1);
-    const int groups = blockDim.x / G;
-    for (int lr = tid / G; lr < nr; lr += groups) {
-        float acc[K][CH][VEC];
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int c = 0; c < CH; ++c)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[k][c][v] = 0.f;
-        const int rs = s_rp[lr], re = s_rp[lr + 1];
-#pragma unroll 2
-        for (int p = rs; p < re; ++p) {
-            int s;
-            float w[K];
-            if (staged) {
-                s = s_col[p - e0];
-                const float* wp = s_w + (size_t)(p - e0) * K;
-                if constexpr (K % 4 == 0) {
-#pragma unroll
-                    for (int k = 0; k < K; k += 4) {
-                        const float4 t = *reinterpret_cast<const float4*>(wp + k);
-                        w[k] = t.x; w[k + 1] = t.y; w[k + 2] = t.z; w[k + 3] = t.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) w[k] = wp[k];
-                }
-            } else {
-                s = __ldg(col + p);
-                const int64_t se = eperm ? (int64_t)__ldg(eperm + p) : (int64_t)p;
-                load_weights<K, 1>(ea + se * Kstride, w);
-            }
-            const bool inwin = (win > 0) && (s >= w0) && (s < w1);
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const int f0 = (c * G + g) * VEC;
-                if (f0 < F) {
-                    float xv[VEC];
-                    if (inwin) {
-                        const float* xs = s_x + (size_t)(s - w0) * F + f0;
-                        if constexpr (VEC == 4) {
-                            const float4 t = *reinterpret_cast<const float4*>(xs);
-                            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-                        } else if constexpr (VEC == 2) {
-                            const float2 t = *reinterpret_cast<const float2*>(xs);
-                            xv[0] = t.x; xv[1] = t.y;
-                        } else {
-                            xv[0] = xs[0];
-                        }
-                    } else {
-                        load_vec<VEC>(x + (int64_t)s * ldx + f0, xv);
-                    }
-#pragma unroll
-                    for (int k = 0; k < K; ++k)
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[k][c][v] = fmaf(w[k], xv[v], acc[k][c][v]);
-                }
-            }
-        }
-        float* orow = out + (int64_t)(r0 + lr) * ldo;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const int f0 = (c * G + g) * VEC;
-            if (f0 < F) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) store_vec<VEC>(orow + (int64_t)k * F + f0, acc[k][c]);
-            }
-        }
-    }
-}
-
 // SDDMM: dea[e(p), k] = <x[col[p]], g[t, k*F:(k+1)*F]>.  The row's K gradient slices stay in registers and
 // each source row is read once per edge; the G lanes of a row reduce by xor-shuffles (all lanes of the warp
 // run the same trip count so the full-mask shuffles are well defined).
@@ -452,24 +322,6 @@ static int k_tile_for(int K, const RowCfg& c) {
     return kt < 1 ? 1 : kt;
 }
 
-// shared-memory plan of the staged kernel for (K tile, F): edge capacity and x-window rows within ~72 KB per CTA
-static void staged_plan(int kt, int F, int vec, int* emax, int* win, size_t* smem) {
-    const size_t budget = 72 * 1024;
-    int em = 1536;
-    while (em > 256 && (size_t)em * (kt + 1) * 4 > budget / 2) em /= 2;
-    size_t fixed = (size_t)em * (kt + 1) * 4 + (SP_ROWS + 1) * 4 + 64;
-    long wrows = ((long)budget - (long)fixed) / ((long)F * 4) - SP_ROWS;
-    int w = (int)(wrows / 2);
-    if (w > 64) w = 64;
-    if (w < 16 || (vec == 2 && F % 2 != 0)) w = 0;      // no room for a useful window: gather from global / L1
-    *emax = em;
-    *win = w;
-    *smem = align_up((size_t)em * kt * 4 + (size_t)(SP_ROWS + 2 * w) * F * 4 + (size_t)em * 4 + (SP_ROWS + 1) * 4, 16);
-}
-
-static int g_spmm_mode = 1;   // 1 = block-staged (default), 0 = direct
-extern "C" void gnnml3_spmm_set_mode(int mode) { g_spmm_mode = mode; }
-
 extern "C" int gnnml3_spmm_k(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea,
                              const float* x, int64_t ldx, int64_t N, int K, int F, float* out, int64_t ldo,
                              void* stream_) {
@@ -481,31 +333,10 @@ extern "C" int gnnml3_spmm_k(const int32_t* rowptr, const int32_t* col, const in
     RowCfg c;
     GNNML3_REQUIRE(pick_cfg(F, a4, a2, &c), "spmm_k: F=%d too wide for this build (max 512 aligned / 128 unaligned)", F);
     const int kt = k_tile_for(K, c);
-    cudaStream_t st = (cudaStream_t)stream_;
-    if (g_spmm_mode == 1) {
-        const int blocks = cdiv(N, SP_ROWS);
-        for (int k0 = 0; k0 < K;) {
-            const int kk = (K - k0 < kt) ? (K - k0) : kt;
-            int emax, win;
-            size_t smem;
-            staged_plan(kk, F, c.vec, &emax, &win, &smem);
-            DISPATCH_K(kk, DISPATCH_VC(c.vec, c.ch, {
-                static size_t configured = 0;
-                if (smem > configured) {
-                    GNNML3_CUDA(cudaFuncSetAttribute(k_spmm_staged<K_, V_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    configured = smem;
-                }
-                k_spmm_staged<K_, V_, C_><<<blocks, 256, smem, st>>>(rowptr, col, eperm, ea + k0, x, ldx, (int)N, F, c.G, K,
-                                                                      out + (int64_t)k0 * F, ldo, emax, win);
-            }));
-            GNNML3_LAUNCH_CHECK();
-            k0 += kk;
-        }
-        return GNNML3_OK;
-    }
     const int rpw = 32 / c.G;
     const int64_t warps = (N + rpw - 1) / rpw;
     const int blocks = (int)((warps + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream_;
     for (int k0 = 0; k0 < K;) {
         const int kk = (K - k0 < kt) ? (K - k0) : kt;
         // widest legal vector load of a tile's weights ea[e*K + k0 .. k0+kk)

@@ -83,9 +83,6 @@ GNNML3_API int gnnml3_scatter_rows(const float* in, const int32_t* perm, int64_t
 GNNML3_API int gnnml3_spmm_k(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea,
                   const float* x, int64_t ldx, int64_t N, int K, int F, float* out, int64_t ldo, void* stream);
 
-/* kernel variant of gnnml3_spmm_k: 1 = block-staged through shared memory (default), 0 = direct (one row per lane group) */
-GNNML3_API void gnnml3_spmm_set_mode(int mode);
-
 /* d ea[e(p), k] = < x[col[p], :], g[t, k*F : (k+1)*F] >  for every edge p of every row t (SDDMM). */
 GNNML3_API int gnnml3_sddmm_k(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* x, int64_t ldx,
                    const float* g, int64_t ldg, int64_t N, int K, int F, float* dea, void* stream);

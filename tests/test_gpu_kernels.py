@@ -112,35 +112,6 @@ def test_spmm_k_matches_oracle(K, F):
     assert_close(out3, refT, name="spmm transposed")
 
 
-@pytest.mark.parametrize("K,F", [(8, 32), (10, 64), (6, 2), (7, 30), (12, 16)])
-def test_spmm_direct_and_staged_variants_agree(K, F):
-    """Both kernel variants (block-staged through shared memory / direct) sum a row in the same order: bit-equal."""
-    from gnn_matlang_b200 import ops, _lib
-    g = torch.Generator().manual_seed(K + F)
-    N, E = 5000, 41000
-    blk = 40
-    src = torch.randint(0, N, (E,), generator=g)
-    dst = ((src // blk) * blk + torch.randint(0, blk, (E,), generator=g)).clamp(max=N - 1)
-    dst[:3000] = 7                                           # one very long row: exceeds the staging buffer
-    src[3000:3300] = torch.randint(0, N, (300,), generator=g)  # sources far outside the window
-    ei = torch.stack([src, dst])
-    x = torch.randn(N, F, generator=g).to(dev())
-    ea = torch.randn(E, K, generator=g).to(dev())
-    csr = ops.csr_build(ei.to(dev()), N)
-    lib = _lib.load()
-    try:
-        lib.gnnml3_spmm_set_mode(0)
-        a = ops.spmm_k(csr["rowptr"], csr["col"], csr["perm"], ea, x)
-        aT = ops.spmm_k(csr["rowptrT"], csr["colT"], csr["permT"], ops.gather_rows(ea, csr["perm"]), x)
-    finally:
-        lib.gnnml3_spmm_set_mode(1)
-    b = ops.spmm_k(csr["rowptr"], csr["col"], csr["perm"], ea, x)
-    bT = ops.spmm_k(csr["rowptrT"], csr["colT"], csr["permT"], ops.gather_rows(ea, csr["perm"]), x)
-    assert torch.equal(a, b) and torch.equal(aT, bT)
-    ref = torch.cat([O.propagate_add(x.cpu(), ei, ea.cpu()[:, k]) for k in range(K)], 1)
-    assert_close(b, ref, name="staged spmm")
-
-
 def test_spmm_k_sequential_order_is_bit_exact_small():
     """Summation inside a row follows the original edge order, like the reference's CPU index_add_."""
     from gnn_matlang_b200 import ops
