@@ -158,6 +158,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # the NCCL version banner goes to stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     kind, cfg, loss, defB, desc = WORKLOADS[args.workload]
     B = args.batch or defB
@@ -303,7 +305,7 @@ def main():
                        "parallelism": "dp%d" % world, "l2_policy": "ring of %d distinct resident batches, %.0f MB in total (> 126 MB L2)" % (args.ring, args.ring * batch_bytes / 1e6),
                        "timed_step": "csr_build + fwd + loss + bwd + (allreduce) + Adam"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "kernel_ms_per_step": breakdown, "final_loss": float(loss_t.item())}))
+            "clocks": sampler.summary(), "kernel_ms_per_step": breakdown, "final_loss": float(loss_t.item())}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
