@@ -13,6 +13,8 @@
 // widths do not idle a warp); each lane holds VEC consecutive features of CH chunks: f = (c*G + g)*VEC + v.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gnnml3 {
 
 template <int K, int WV>
@@ -240,6 +242,11 @@ struct RowCfg {
     int vec, G, ch;
 };
 
+static const bool g_wide_rows = [] {
+    const char* e = getenv("GNNML3_SPMM_WIDE");
+    return e ? (e[0] != '0') : true;
+}();
+
 static bool pick_cfg(int F, bool aligned4, bool aligned2, RowCfg* c) {
     int vec = (F % 4 == 0 && aligned4) ? 4 : ((F % 2 == 0 && aligned2) ? 2 : 1);
     int units = F / vec;
@@ -255,6 +262,12 @@ static bool pick_cfg(int F, bool aligned4, bool aligned2, RowCfg* c) {
         ch = (units + 31) / 32;
         if (ch == 3) ch = 4;
         if (ch > 4) return false;
+    }
+    // fewer lanes per row, two chunks per lane: halves the per-edge index / address / loop overhead per FMA
+    // (the kernels are instruction-issue and latency bound, not bandwidth bound) and doubles the rows per warp
+    if (ch == 1 && G >= 8 && g_wide_rows) {
+        G >>= 1;
+        ch = 2;
     }
     c->vec = vec;
     c->G = G;
@@ -302,6 +315,7 @@ using namespace gnnml3;
     else if (VEC == 4 && CH == 2) { constexpr int V_ = 4, C_ = 2; __VA_ARGS__; }           \
     else if (VEC == 4 && CH == 4) { constexpr int V_ = 4, C_ = 4; __VA_ARGS__; }           \
     else if (VEC == 2 && CH == 1) { constexpr int V_ = 2, C_ = 1; __VA_ARGS__; }           \
+    else if (VEC == 2 && CH == 2) { constexpr int V_ = 2, C_ = 2; __VA_ARGS__; }           \
     else if (VEC == 1 && CH == 1) { constexpr int V_ = 1, C_ = 1; __VA_ARGS__; }           \
     else if (VEC == 1 && CH == 2) { constexpr int V_ = 1, C_ = 2; __VA_ARGS__; }           \
     else if (VEC == 1 && CH == 4) { constexpr int V_ = 1, C_ = 4; __VA_ARGS__; }           \
