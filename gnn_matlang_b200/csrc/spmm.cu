@@ -85,9 +85,9 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ col, const int* _
     const int rs = __ldg(rowptr + row), re = __ldg(rowptr + row + 1);
     // U edges per iteration: all index, weight and source-row loads of the U edges are issued before the first FMA,
     // so a lane keeps U * (CH + K/WV) independent 64/128-bit loads in flight (rows are short -- 5..20 edges -- and
-    // the index -> gather chain would otherwise serialise on memory latency).  Edges past the end of the row are
-    // predicated off with zero weights.
-    constexpr int U = (K * VEC * CH <= 32) ? 4 : 2;
+    // the index -> gather chain would otherwise serialise on memory latency).  Slots past the end of the row load a
+    // clamped (valid) edge and skip the FMAs.
+    constexpr int U = 2;   // measured on B200: 2 beats 4 (rows hold ~6 edges; slots past the row end still cost their loads)
     for (int p0 = rs; p0 < re; p0 += U) {
         int sidx[U], eidx[U];
 #pragma unroll
