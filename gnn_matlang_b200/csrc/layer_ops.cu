@@ -92,6 +92,56 @@ k_ml3_act_bwd(const float* __restrict__ pre, int64_t ldp, const float* __restric
     }
 }
 
+// Same gradient from the OUTPUTS of the fused layer kernel (fused_layer.cu): the ReLU mask is y > 0 and the gate factors
+// t1 = tanh(p1), t2 = tanh(p2) were saved in aux [N, 2G], so `pre` is never materialised.  gpre uses the layout the fused
+// dx kernel gathers from: conv gradient in columns [0, Fo), zero padding to Fo4 = ceil4(Fo), gate gradients
+// [g1 | g2] in [Fo4, Fo4 + 2G), zero padding up to the row stride ldg (all 16-byte aligned blocks).  colpart as above,
+// in the logical order [conv | g1 | g2].
+__global__ void __launch_bounds__(256)
+k_ml3_act_bwd_y(const float* __restrict__ y, int64_t ldy, const float* __restrict__ aux, int64_t ldaux,
+                const float* __restrict__ gy, int64_t ldgy, int64_t N, int Fo, int G, float* __restrict__ gpre, int64_t ldg,
+                float* __restrict__ colpart) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int Fo4 = (Fo + 3) / 4 * 4, W2 = Fo + 2 * G;
+    const int64_t r0 = (int64_t)blockIdx.x * ACT_ROWS;
+    const int64_t r1 = min(N, r0 + ACT_ROWS);
+    for (int c0 = 0; c0 < (int)ldg; c0 += 32) {
+        const int c = c0 + tx;
+        int kind = 3, j = 0;                    // 0 conv, 1 gate 1, 2 gate 2, 3 padding
+        if (c < Fo) kind = 0;
+        else if (c >= Fo4 && c < Fo4 + G) { kind = 1; j = c - Fo4; }
+        else if (c >= Fo4 + G && c < Fo4 + 2 * G) { kind = 2; j = c - Fo4 - G; }
+        float s = 0.f;
+        if (c < (int)ldg) {
+            for (int64_t n = r0 + ty; n < r1; n += 8) {
+                float v = 0.f;
+                if (kind == 0) {
+                    v = __ldg(y + n * ldy + c) > 0.f ? __ldg(gy + n * ldgy + c) : 0.f;
+                } else if (kind != 3) {
+                    const float g = __ldg(gy + n * ldgy + Fo + j);
+                    const float t1 = __ldg(aux + n * ldaux + j), t2 = __ldg(aux + n * ldaux + G + j);
+                    v = kind == 1 ? g * t2 * (1.f - t1 * t1) : g * t1 * (1.f - t2 * t2);
+                }
+                gpre[n * ldg + c] = v;
+                s += v;
+            }
+        }
+        if (colpart) {
+            red[ty][tx] = s;
+            __syncthreads();
+            if (ty == 0 && kind != 3) {
+                float v = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v += red[q][tx];
+                const int lc = kind == 0 ? c : (kind == 1 ? Fo + j : Fo + G + j);
+                colpart[(int64_t)blockIdx.x * W2 + lc] = v;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void k_colsum_finish(const float* __restrict__ part, int nblocks, int W2, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= W2) return;
@@ -200,5 +250,35 @@ extern "C" int gnnml3_segment_pool_bwd(const float* gout, const int32_t* graph_p
     const int64_t warps = (int64_t)B * ((F + 31) / 32);
     k_segment_pool_bwd<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(gout, graph_ptr, B, F, mean, gx, ldx);
     GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+extern "C" int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* aux, int64_t ldaux, const float* gy, int64_t ldgy,
+                                    int64_t N, int Fo, int G, float* gpre, int64_t ldg, float* colsum, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+    GNNML3_REQUIRE(N >= 0 && Fo >= 1 && G >= 0, "ml3_act_bwd_y: bad shape");
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (N == 0) {
+        if (colsum) GNNML3_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * (Fo + 2 * G), st));
+        return GNNML3_OK;
+    }
+    const int Fo4 = (Fo + 3) / 4 * 4;
+    GNNML3_REQUIRE(y && gy && gpre && ldy >= Fo && ldgy >= Fo + G && ldg >= Fo4 + 2 * G && ldg <= 4096,
+                   "ml3_act_bwd_y: bad arguments");
+    GNNML3_REQUIRE(G == 0 || (aux && ldaux >= 2 * G), "ml3_act_bwd_y: aux [N, 2G] required");
+    float* part = nullptr;
+    if (colsum) {
+        GNNML3_REQUIRE(workspace, "ml3_act_bwd_y: workspace required for the column sums");
+        if (workspace_bytes < gnnml3_ml3_act_bwd_workspace_bytes(N, Fo, G))
+            return set_err(GNNML3_ERR_WORKSPACE, "ml3_act_bwd_y: workspace too small");
+        part = (float*)workspace;
+    }
+    const int nb = cdiv(N, ACT_ROWS);
+    k_ml3_act_bwd_y<<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part);
+    GNNML3_LAUNCH_CHECK();
+    if (colsum) {
+        k_colsum_finish<<<cdiv(Fo + 2 * G, 128), 128, 0, st>>>(part, nb, Fo + 2 * G, colsum);
+        GNNML3_LAUNCH_CHECK();
+    }
     return GNNML3_OK;
 }

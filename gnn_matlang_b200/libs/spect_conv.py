@@ -15,6 +15,7 @@ transposed CSR)  dx = [G_0..G_{K-1}] W'^T,  dW_k = x^T G_k,  d edge_attr = SDDMM
 All arithmetic happens in libgnnml3_b200.so; there is no CPU fallback (CPU tensors raise RuntimeError).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -24,6 +25,12 @@ from .. import _lib, ops
 from ..graph import get_plan, sorted_edge_attr
 
 _PRECISIONS = {"fp32": _lib.PREC_3XTF32, "3xtf32": _lib.PREC_3XTF32, "tf32": _lib.PREC_TF32}
+USE_FUSED = os.environ.get("GNNML3_NO_FUSED", "0") != "1"
+
+
+def _use_fused(precision):
+    """The fused tcgen05 layer kernel implements the FP32-grade (3xTF32) arithmetic only."""
+    return USE_FUSED and precision == _lib.PREC_3XTF32
 
 
 def glorot(tensor):
@@ -176,7 +183,9 @@ class _ML3LayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ea_s, w1, w2, w3, w4, wconv, bconv, w11, b11, w12, b12, plan, fused_edge, precision):
-        x, ea_s = x.contiguous(), ea_s.contiguous()
+        if x.stride(1) != 1:        # row-strided views (padded layer outputs) are consumed as they are
+            x = x.contiguous()
+        ea_s = ea_s.contiguous()
         wconv = wconv.contiguous()
         N, Fi = x.shape
         K, _, Fo = wconv.shape
@@ -186,6 +195,22 @@ class _ML3LayerFn(torch.autograd.Function):
             ea2 = ops.edge_mlp_fwd(ea_s, None, w1, w2, w3, w4)
         else:
             ea2 = ea_s
+        fused = (_use_fused(precision) and N > 0 and plan.E > 0 and (G == 0 or Fi <= 32)
+                 and ops.fused_supported(K, K, Fi, Fo, Fi if G else 0, 1 if G else 0, 2 * G)
+                 and ops.fused_supported(K, K, Fo, Fi, 2 * G, 2 if G else 0, 0))
+        ctx.plan, ctx.fused_edge, ctx.precision, ctx.G = plan, fused_edge, precision, G
+        ctx.has_bias = bconv is not None
+        ctx.fused = fused
+        if fused:
+            # aggregate + project + gate linears + activations in ONE kernel (fused_layer.cu); H and pre never exist
+            xa = ops.aligned_rows(x)
+            wg = torch.cat([w11.t(), w12.t()], 1).contiguous() if G > 0 else None
+            bg = torch.cat([b11, b12]) if G > 0 else None
+            y, aux = ops.fused_agg_proj(plan.rowptr, plan.col, None, ea2, xa, wconv.view(K * Fi, Fo), bias=bconv,
+                                        S=xa if G > 0 else None, self_mode=1 if G > 0 else 0, Bself=wg, bias_s=bg, G=G,
+                                        epilogue=1)
+            ctx.save_for_backward(xa, ea_s, ea2 if fused_edge else None, y, aux, w1, w2, w3, w4, wconv, w11, w12)
+            return y
         H = _aggregate(plan, ea2, x, K)
         # rows padded to a multiple of 4 floats so that the GEMM epilogues can store 128-bit vectors
         pre = torch.empty(N, (Fo + 2 * G + 3) // 4 * 4, dtype=torch.float32, device=x.device)[:, :Fo + 2 * G]
@@ -195,14 +220,12 @@ class _ML3LayerFn(torch.autograd.Function):
                 wg = torch.cat([w11.t(), w12.t()], 1).contiguous()
                 ops.gemm_nn(x, wg, torch.cat([b11, b12]), precision=precision, out=pre[:, Fo:])
         y = ops.ml3_act_fwd(pre, Fo, G)
-        ctx.save_for_backward(x, ea_s, ea2 if fused_edge else None, pre, w1, w2, w3, w4, wconv, w11, w12)
-        ctx.plan, ctx.fused_edge, ctx.precision, ctx.G = plan, fused_edge, precision, G
-        ctx.has_bias = bconv is not None
+        ctx.save_for_backward(x, ea_s, ea2 if fused_edge else None, pre, None, w1, w2, w3, w4, wconv, w11, w12)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, ea_s, ea2, pre, w1, w2, w3, w4, wconv, w11, w12 = ctx.saved_tensors
+        x, ea_s, ea2, pre, aux, w1, w2, w3, w4, wconv, w11, w12 = ctx.saved_tensors
         plan, prec, G = ctx.plan, ctx.precision, ctx.G
         if ea2 is None:
             ea2 = ea_s
@@ -211,7 +234,14 @@ class _ML3LayerFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         gy = gy.contiguous()
         Gp = torch.empty(N, K * Fo + 2 * G, dtype=torch.float32, device=x.device)
-        gpre, dball = ops.ml3_act_bwd(pre, gy, Fo, G, gate_out=Gp[:, K * Fo:] if G > 0 else None)
+        if ctx.fused:
+            # `pre` holds the layer OUTPUT y here; gpre = [gc | 0 | g1 g2 | 0] with the gate block at column ceil4(Fo)
+            Fo4 = (Fo + 3) // 4 * 4
+            gpre, dball = ops.ml3_act_bwd_y(pre, aux, gy, Fo, G)
+            if G > 0:
+                Gp[:, K * Fo:] = gpre[:, Fo4:Fo4 + 2 * G]
+        else:
+            gpre, dball = ops.ml3_act_bwd(pre, gy, Fo, G, gate_out=Gp[:, K * Fo:] if G > 0 else None)
         gc = gpre[:, :Fo]
         dx = dea = None
         dws = [None, None, None, None]
@@ -226,7 +256,14 @@ class _ML3LayerFn(torch.autograd.Function):
             Gp[:, :K * Fo].zero_()
         else:
             ops.spmm_k(plan.rowptrT, plan.colT, plan.permT, ea2, gc, out=Gp)
-        if need[0]:
+        if need[0] and ctx.fused:
+            # dx = sum_k S_k^T gc W_k^T + g1 W11 + g2 W12: the fused kernel over the transposed CSR, gate gradients as
+            # one more k-block accumulating into the same columns
+            dx, _ = ops.fused_agg_proj(plan.rowptrT, plan.colT, plan.permT, ea2, gpre[:, :Fo],
+                                       wconv.transpose(1, 2).reshape(K * Fo, Fi).contiguous(),
+                                       S=gpre[:, Fo4:Fo4 + 2 * G] if G > 0 else None, self_mode=2 if G > 0 else 0,
+                                       Bself=torch.cat([w11, w12], 0).contiguous() if G > 0 else None, epilogue=0)
+        elif need[0]:
             blocks = [wconv.transpose(1, 2).reshape(K * Fo, Fi)]
             if G > 0:
                 blocks += [w11, w12]

@@ -280,6 +280,82 @@ def ml3_act_bwd(pre, gy, Fo, G, gate_out=None):
     return gpre, csum
 
 
+def aligned_rows(t):
+    """float32 CUDA matrix with unit column stride, row stride % 4 == 0 and a 16-byte aligned base (what the 128-bit
+    gathers of the fused kernels need); otherwise a zero-padded copy [N, ceil4(F)] (data movement only)."""
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise RuntimeError("expected a float32 CUDA tensor: gnn_matlang_b200 has no CPU fallback")
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 and t.stride(0) >= t.size(1):
+        return t
+    N, F = t.shape
+    buf = torch.zeros(N, (F + 3) // 4 * 4, dtype=torch.float32, device=t.device)
+    buf[:, :F] = t
+    return buf[:, :F]
+
+
+def fused_supported(K, Kstride, F, Nc, Fs=0, self_mode=0, Ns=0):
+    return bool(_lib.load().gnnml3_fused_supported(int(K), int(Kstride), int(F), int(Nc), int(Fs), int(self_mode), int(Ns)))
+
+
+def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mode=0, Bself=None, bias_s=None, G=0,
+                   epilogue=0):
+    """Fused aggregate + project (gnnml3_fused_agg_proj).  x [*, F] and S [N, Fs] must satisfy ``aligned_rows``.
+    epilogue 0 -> out [N, Nc];  epilogue 1 -> (y [N, Nc + G], aux [N, 2G]) = the ML3Layer node branch."""
+    lib = _lib.load()
+    ea = _f32c(ea, "edge_attr")
+    Bmain = _f32c(Bmain, "Bmain")
+    N = rowptr.numel() - 1
+    F, K = x.size(1), ea.size(1)
+    Nc = Bmain.size(1)
+    if Bmain.size(0) != K * F:
+        raise RuntimeError("fused_agg_proj: Bmain must be [K*F, Nc] = [%d, %d], got %s" % (K * F, Nc, tuple(Bmain.shape)))
+    Fs = Ns = 0
+    if self_mode:
+        Bself = _f32c(Bself, "Bself")
+        Fs, Ns = S.size(1), Bself.size(1)
+        if Bself.size(0) != Fs:
+            raise RuntimeError("fused_agg_proj: Bself must have %d rows" % Fs)
+    dev = x.device
+    W = Nc + (G if self_mode == 1 else 0)
+    ldo = (W + 3) // 4 * 4
+    out = torch.empty(N, ldo, dtype=torch.float32, device=dev)
+    if ldo != W:
+        out[:, W:].zero_()          # padding columns are read (and multiplied by zero weights) by the next fused gather
+    out = out[:, :W]
+    aux = torch.empty(N, 2 * G, dtype=torch.float32, device=dev) if self_mode == 1 else None
+    if bias is not None:
+        bias = _f32c(bias, "bias")
+    if bias_s is not None:
+        bias_s = _f32c(bias_s, "bias_s")
+    ws = _ws(dev, lib.gnnml3_fused_workspace_bytes(K, F, Nc, self_mode), tag="fused")
+    with torch.cuda.device(dev):
+        _lib.check(lib.gnnml3_fused_agg_proj(
+            _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(ea), K, K, _lib.ptr(x), _ld(x), F,
+            _lib.ptr(S) if self_mode else None, _ld(S) if self_mode else 0, Fs, self_mode, _lib.ptr(Bmain), _ld(Bmain),
+            _lib.ptr(Bself) if self_mode else None, _ld(Bself) if self_mode else 0, Ns, _lib.ptr(bias), _lib.ptr(bias_s),
+            N, Nc, _lib.ptr(out), ldo, _lib.ptr(aux), 2 * G, G, epilogue, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            "gnnml3_fused_agg_proj")
+    return out, aux
+
+
+def ml3_act_bwd_y(y, aux, gy, Fo, G):
+    """d pre from the fused layer's outputs -> (gpre [N, ldg] in the layout [conv | 0.. | g1 g2 | 0..] with the gate block
+    at column ceil4(Fo), column sums [Fo + 2G] = bias gradients)."""
+    lib = _lib.load()
+    gy = _rows(gy, "gy")
+    N = y.size(0)
+    Fo4 = (Fo + 3) // 4 * 4
+    ldg = (Fo4 + 2 * G + 3) // 4 * 4
+    gpre = torch.empty(N, ldg, dtype=torch.float32, device=y.device)
+    csum = torch.empty(Fo + 2 * G, dtype=torch.float32, device=y.device)
+    ws = _ws(y.device, lib.gnnml3_ml3_act_bwd_workspace_bytes(N, Fo, G))
+    with torch.cuda.device(y.device):
+        _lib.check(lib.gnnml3_ml3_act_bwd_y(_lib.ptr(y), _ld(y), _lib.ptr(aux), 2 * G, _lib.ptr(gy), _ld(gy), N, Fo, G,
+                                            _lib.ptr(gpre), ldg, _lib.ptr(csum), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "gnnml3_ml3_act_bwd_y")
+    return gpre, csum
+
+
 def segment_pool_fwd(x, graph_ptr, mean):
     lib = _lib.load()
     x = _f32c(x, "x")
@@ -338,5 +414,6 @@ def _instrument(name, fn):
 
 
 for _n in ("csr_build", "gather_rows", "scatter_rows", "spmm_k", "sddmm_k", "gemm_nn_tc", "gemm_nn", "gemm_tn", "colsum", "edge_mlp_fwd",
-           "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "segment_pool_fwd", "segment_pool_bwd"):
+           "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "ml3_act_bwd_y", "fused_agg_proj", "segment_pool_fwd",
+           "segment_pool_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

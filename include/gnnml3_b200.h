@@ -129,6 +129,33 @@ GNNML3_API int gnnml3_ml3_act_bwd(const float* pre, int64_t ldp, const float* gy
                        float* gpre, int64_t ldg, float* gate_out, int64_t ldgate, float* colsum,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same gradient from the outputs of gnnml3_fused_agg_proj (ReLU mask = y > 0, aux = [tanh(p1) | tanh(p2)]).  gpre layout:
+ * conv gradient in columns [0, Fo), zeros to Fo4 = ceil4(Fo), gate gradients [g1 | g2] in [Fo4, Fo4 + 2G), zeros up to ldg --
+ * the 16-byte aligned blocks the fused dx kernel gathers.  colsum in the logical order [conv | g1 | g2]. */
+GNNML3_API int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* aux, int64_t ldaux, const float* gy, int64_t ldgy,
+                         int64_t N, int Fo, int G, float* gpre, int64_t ldg, float* colsum,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused aggregate + project on tcgen05 / TMEM (fused_layer.cu): for every row t of the CSR
+ *   main[t, :] = sum_k ( sum_{p in row t} ea[e(p), k] * X[col[p], :] ) Bmain[k*F:(k+1)*F, :]   (+ bias)
+ * without materialising the [N, K*F] aggregate (libs/spect_conv.py:70-80,93-94).  Optional self block S [N, Fs]:
+ *   self_mode 1: own output columns  s[t, :] = S[t, :] Bself [Fs, Ns = 2G] (+ bias_s)  -- with epilogue 1 this is the whole
+ *                ML3Layer node branch (:208-212): out[t] = [relu(main) || tanh(s[:G]) * tanh(s[G:])], aux[t] = tanh(s);
+ *   self_mode 2: main[t, :] += S[t, :] Bself [Fs, Nc]  (SpectConv selfconn; gate gradients in the dx pass).
+ * epilogue 0: out [N, Nc] = main.  X and S rows must be 16-byte aligned (ld % 4 == 0) and every column below
+ * ceil4(F) / ceil4(Fs) must hold finite values.  3xTF32 arithmetic (FP32-grade).  Backward dx = the same call over the
+ * transposed CSR with X = d pre, Bmain = W_k^T.
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_fused_supported(int K, int Kstride, int F, int Nc, int Fs, int self_mode, int Ns);
+GNNML3_API size_t gnnml3_fused_workspace_bytes(int K, int F, int Nc, int self_mode);
+GNNML3_API int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea,
+                          int Kstride, int K, const float* X, int64_t ldx, int F, const float* S, int64_t lds,
+                          int Fs, int self_mode, const float* Bmain, int64_t ldb, const float* Bself,
+                          int64_t ldbs, int Ns, const float* bias, const float* bias_s, int64_t N, int Nc,
+                          float* out, int64_t ldo, float* aux, int64_t ldaux, int G, int epilogue,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Readout: PyG global_add_pool (mean = 0) / global_mean_pool (mean = 1) over contiguous node ranges
  * graph_ptr [B+1] (graph b owns nodes graph_ptr[b] .. graph_ptr[b+1]-1, as produced by batching).
