@@ -5,15 +5,20 @@
 //     y[t, :]    = [ relu(conv[t, :]) || tanh(x[t] W11^T + b11) * tanh(x[t] W12^T + b12) ]    (ML3Layer)
 // The reference materialises K message tensors [E, Fi], K scatter results [N, Fi] and K matmul results; the
 // two-kernel design of spmm.cu + gemm*.cu still round-trips H = [P_0(x) .. P_{K-1}(x)]  ([N, K*Fi]) through HBM.
-// Here H never leaves the SM: a persistent CTA owns a tile of dst rows,
+// Here H never leaves the SM: a persistent CTA owns a tile of ROWS dst rows,
 //   * aggregator warps walk the tile's CSR rows (4 lanes per row, 8 features per lane, KT supports in registers,
 //     128-bit gathers of the source rows, summation in edge order, no atomics) and write each 32-column block
 //     of H straight into shared memory in the UMMA K-major SWIZZLE_128B layout, as the raw FP32 plane (= the hi
-//     part: the tensor core truncates to TF32 itself) and the residual plane lo = a - trunc(a);
-//   * one thread issues tcgen05.mma kind::tf32 (lo*hi + hi*lo + hi*hi: FP32-grade 3xTF32) against the pre-split
-//     weight planes that a TMA warp streams from L2; accumulators live in tensor memory;
-//   * epilogue warps drain TMEM (round-to-nearest chunk sums), add the bias and apply ReLU / tanh*tanh gating,
-//     writing y (and the two tanh factors the backward needs) -- or a plain [N, Nc] result.
+//     part: the tensor core truncates to TF32 itself) and, right behind it, the residual plane lo = a - trunc(a);
+//   * one thread issues tcgen05.mma kind::tf32.  A tcgen05.mma costs ~143 cycles on B200 whatever its shape
+//     (measured, scratch/umma_bench.cu), so the operands are arranged to make every instruction as large as
+//     possible: the weights are the M side -- rows [W_hi^T ; W_lo^T ; gate weights hi ; lo] of one 128-row plane per
+//     k-block, streamed from L2 by a TMA warp -- and the tile's rows are the N side, hi and lo planes side by side
+//     (N = 2 * ROWS).  ONE instruction per 8-wide k-step therefore produces all four products
+//     {W_hi, W_lo} x {H_hi, H_lo} of the error-compensated 3xTF32 split (FP32-grade) for the whole tile;
+//   * epilogue warps drain the transposed accumulator D[feature, row] from tensor memory, add the hi/lo partial
+//     sums (pairs of warps exchange through shared memory), add the bias, apply ReLU / tanh*tanh gating and write
+//     y (and the two tanh factors the backward needs) with fully coalesced 128-byte row stores.
 // The same kernel computes dx in the backward: rows = source nodes over the transposed CSR, gathered matrix =
 // d pre (conv columns), weights = W_k^T, and the gate gradients enter as one more k-block ("self" block) that
 // accumulates into the same output columns.  SpectConv(selfconn=True) uses that mode in the forward, too.
@@ -21,18 +26,9 @@
 
 namespace gnnml3 {
 
-constexpr int FL_STAGES = 4;
-constexpr int FL_PLANE = 128 * 128;   // bytes of one [128 rows x 32 FP32] k-block plane
+constexpr int FL_MAX_STAGES = 4;
 constexpr int FL_CTRL_WARPS = 6;      // warps 0-3: epilogue | warp 4: TMA (weights) | warp 5: MMA issuer | then aggregators
-
-template <int BN>
-struct FLCfg {
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = 2 * FL_PLANE + 2 * B_BYTES;     // A raw | A lo | B hi | B lo
-    static constexpr int NBUF = 256 / BN;                              // TMEM chunk buffers
-    static constexpr int TMEM_COLS = 256;
-    static constexpr size_t SMEM = (size_t)FL_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
-};
+constexpr int FL_XCH = 32 * 68 + 8;    // half the floats of the epilogue's transpose tile T (>= 32 x 132 in total)
 
 struct FLParams {
     const int* rowptr;      // [N+1] CSR over the rows of this launch
@@ -46,13 +42,13 @@ struct FLParams {
     const float* S;         // self block [N, Fs] (row t of the tile itself), NULL if self_mode == 0
     int64_t lds;
     int Fs;
-    int self_mode;          // 0 none | 1 own output columns (BNS wide: the ML3 gates) | 2 accumulates into the main columns
-    int BNS;                // MMA N of the self block in mode 1 (16 or 32)
+    int self_mode;          // 0 none | 1 own output columns (the ML3 gates, M rows 64..127) | 2 accumulates into the main columns
     int64_t N;
     int n_tiles;
     int nfh;                // 32-wide feature blocks per support = ceil(F / 32)
     int nkb_main;           // nfh * K
-    int chunk_kb;           // k-blocks per TMEM chunk
+    int pf_rows;            // rows of X prefetched into L1 on either side of a tile (0: off)
+    int nstages;            // depth of the H-plane ring (2..4, whatever shared memory is left beside resident weights)
     const float* bias;      // [Nc] or NULL
     const float* bias_s;    // [2G] or NULL (mode 1)
     float* out;             // plain: [N, Nc]; ml3: y [N, Fo + G]
@@ -62,6 +58,7 @@ struct FLParams {
     int64_t ldaux;
     int G;
     int epi;                // 0 plain (+bias) | 1 ml3: relu on the main columns, gating on the self columns
+    unsigned long long* dbg; // optional cycle counters (GNNML3_FUSED_DEBUG=1): see gnnml3_fused_debug_counters
 };
 
 template <int KT>
@@ -86,207 +83,261 @@ __device__ __forceinline__ void fl_load_ea(const float* __restrict__ p, float (&
 
 __device__ __forceinline__ float fl_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-// raw plane + residual plane of one 16-byte chunk
+// raw plane + residual plane (LO_OFF bytes behind it) of one 16-byte chunk
+template <int LO_OFF>
 __device__ __forceinline__ void fl_store_chunk(uint8_t* a_raw, uint32_t off, const float* v) {
     *reinterpret_cast<float4*>(a_raw + off) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(a_raw + FL_PLANE + off) = make_float4(fl_lo(v[0]), fl_lo(v[1]), fl_lo(v[2]), fl_lo(v[3]));
+    *reinterpret_cast<float4*>(a_raw + LO_OFF + off) = make_float4(fl_lo(v[0]), fl_lo(v[1]), fl_lo(v[2]), fl_lo(v[3]));
 }
 
-template <int KT, int BN, int NAGG>
+// BNH = output columns per hi/lo half of the weight plane's M side: 32 (Nc <= 32: M = 64, rows [W_hi^T ; W_lo^T]; the ML3
+// gate weights form a second M = 64 operand whose accumulator interleaves with the main one in tensor memory at a lane
+// offset of 16) or 64 (Nc <= 64: M = 128, no gates).  RES: all weight planes stay resident in shared memory (loaded once);
+// otherwise the plane of every k-block is streamed from L2 into the stage.
+template <int KT, int BNH, int NAGG, bool RES>
 __global__ void __launch_bounds__(32 * (FL_CTRL_WARPS + NAGG), 1)
-k_fused_agg_proj(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-                 const __grid_constant__ CUtensorMap mapShi, const __grid_constant__ CUtensorMap mapSlo,
-                 const __grid_constant__ FLParams P) {
-    using Cfg = FLCfg<BN>;
-    constexpr int NBUF = Cfg::NBUF;
-    constexpr int ROWS = 8 * NAGG;                      // dst rows per tile (<= 128 = the MMA's M)
-    static_assert(ROWS <= 128, "tile rows exceed the MMA M");
+k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ FLParams P) {
+    constexpr int ROWS = 8 * NAGG;                      // dst rows per tile
+    constexpr int NMMA = 2 * ROWS;                      // MMA N: hi plane rows then lo plane rows
+    constexpr int MROWS = 2 * BNH;                      // MMA M: weight-plane rows
+    constexpr int WPLANE = MROWS * 128;                 // bytes of one weight plane
+    constexpr int HP_BYTES = 2 * ROWS * 128;            // both H planes of a k-block
+    constexpr int STAGE_BYTES = HP_BYTES + (RES ? 0 : WPLANE);
+    static_assert(NMMA <= 256 && NMMA % 16 == 0, "bad tile size");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)FL_STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;                             // [STAGES]  A planes written + weight bytes landed -> MMA
-    uint64_t* empty = bars + FL_STAGES;                // [STAGES]  MMAs retired                           -> writers
-    uint64_t* tfull = bars + 2 * FL_STAGES;            // [NBUF]    accumulator chunk complete             -> epilogue
-    uint64_t* tempty = bars + 2 * FL_STAGES + NBUF;    // [NBUF]    accumulator drained                    -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FL_STAGES + 2 * NBUF);
+    const int nkb_total = P.nkb_main + (P.self_mode != 0 ? 1 : 0);
+    const int nstages = P.nstages;
+    uint8_t* wres = smem;                                                               // [nkb_total][WPLANE] if RES
+    uint8_t* stages = smem + (RES ? (size_t)nkb_total * WPLANE : 0);
+    float* xch = reinterpret_cast<float*>(stages + (size_t)nstages * STAGE_BYTES);      // [2 pairs][2][32][33]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * FL_XCH);
+    uint64_t* full = bars;                             // [STAGES]  H planes written (+ weight bytes landed) -> MMA
+    uint64_t* empty = bars + FL_MAX_STAGES;            // [STAGES]  MMAs retired                             -> writers
+    uint64_t* tfull = bars + 2 * FL_MAX_STAGES;        // [2]       tile accumulator complete                -> epilogue
+    uint64_t* tempty = bars + 2 * FL_MAX_STAGES + 2;   // [2]       accumulator drained                      -> MMA
+    uint64_t* wfull = bars + 2 * FL_MAX_STAGES + 4;    // [1]       resident weights landed                  -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FL_MAX_STAGES + 5);
+    int* agg_seq = reinterpret_cast<int*>(tmem_slot + 1);      // tiles started by the aggregators (paces the prefetch warp)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb_chain = P.nkb_main + (P.self_mode == 2 ? 1 : 0);     // k-blocks accumulated into the main columns
-    const int nkb_total = P.nkb_main + (P.self_mode != 0 ? 1 : 0);
 
-    // rows ROWS..127 of the A planes are never written: clear them once so that no NaN pattern is ever multiplied
-    for (int i = threadIdx.x; i < FL_STAGES * Cfg::STAGE_BYTES / 16; i += blockDim.x)
-        reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < FL_STAGES; ++s) {
-            mbar_init(full + s, NAGG + 1);
+        for (int s = 0; s < FL_MAX_STAGES; ++s) {
+            mbar_init(full + s, NAGG + (RES ? 0 : 1));
             mbar_init(empty + s, 1);
         }
-        for (int b = 0; b < NBUF; ++b) {
+        for (int b = 0; b < 2; ++b) {
             mbar_init(tfull + b, 1);
             mbar_init(tempty + b, 4);
         }
+        mbar_init(wfull, 1);
+        *agg_seq = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
     }
-    if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    fence_proxy_async_smem();
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        // =================================================================== TMA: weight planes of every k-block
+        // =================================================================== TMA: weight planes (+ L2 prefetch of the edge data)
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                for (int kb = 0; kb < nkb_total; ++kb, ++it) {
-                    const int s = it % FL_STAGES;
-                    mbar_wait(empty + s, ((it / FL_STAGES) & 1) ^ 1);
-                    uint8_t* st = smem + (size_t)s * Cfg::STAGE_BYTES + 2 * FL_PLANE;
-                    if (kb < nkb_chain) {
-                        mbar_arrive_expect_tx(full + s, 2 * Cfg::B_BYTES);
-                        tma_load_2d(st, &mapBhi, full + s, 0, kb * BN);
-                        tma_load_2d(st + Cfg::B_BYTES, &mapBlo, full + s, 0, kb * BN);
-                    } else {
-                        mbar_arrive_expect_tx(full + s, 2 * P.BNS * 128);
-                        tma_load_2d(st, &mapShi, full + s, 0, 0);
-                        tma_load_2d(st + Cfg::B_BYTES, &mapSlo, full + s, 0, 0);
+            if constexpr (RES) {
+                mbar_arrive_expect_tx(wfull, (uint32_t)nkb_total * WPLANE);
+                for (int kb = 0; kb < nkb_total; ++kb)
+                    tma_load_2d(wres + (size_t)kb * WPLANE, &mapW, wfull, 0, kb * MROWS);
+            } else {
+                uint32_t it = 0;
+                for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                    for (int kb = 0; kb < nkb_total; ++kb, ++it) {
+                        const uint32_t s = it % nstages;
+                        mbar_wait(empty + s, ((it / nstages) & 1) ^ 1);
+                        mbar_arrive_expect_tx(full + s, WPLANE);
+                        tma_load_2d(stages + (size_t)s * STAGE_BYTES + HP_BYTES, &mapW, full + s, 0, kb * MROWS);
                     }
+                }
+            }
+        }
+        if constexpr (RES) {
+            // The warp is idle from here on: it stays one tile ahead of the aggregators and pulls the next tile's CSR slots,
+            // edge weights (contiguous per tile when eperm == NULL) and the block of X rows around the tile (the sources of a
+            // batched disjoint graph lie within a graph's size of their targets) into L1, so that the aggregators' dependent
+            // gathers hit L1 instead of paying an L2 / HBM round trip per edge pair.  Purely a hint: wrong guesses cost nothing.
+            __syncwarp();
+            int j = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++j) {
+                while (*reinterpret_cast<volatile int*>(agg_seq) < j - 1) __nanosleep(64);
+                const int64_t r0 = (int64_t)tile * ROWS;
+                const int64_t r1 = r0 + ROWS < P.N ? r0 + ROWS : P.N;
+                const int e0 = __ldg(P.rowptr + r0), e1 = __ldg(P.rowptr + r1);
+                const char* pc = reinterpret_cast<const char*>(P.col + e0);
+                const int64_t nbc = (int64_t)(e1 - e0) * 4;
+                for (int64_t o = (int64_t)lane * 128; o < nbc; o += 32 * 128)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pc + o));
+                if (P.eperm) {
+                    const char* pp = reinterpret_cast<const char*>(P.eperm + e0);
+                    for (int64_t o = (int64_t)lane * 128; o < nbc; o += 32 * 128)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + o));
+                } else {
+                    const char* pe = reinterpret_cast<const char*>(P.ea + (int64_t)e0 * P.Kstride);
+                    const int64_t nbe = (int64_t)(e1 - e0) * P.Kstride * 4;
+                    for (int64_t o = (int64_t)lane * 128; o < nbe; o += 32 * 128)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pe + o));
+                }
+                if (P.pf_rows > 0) {
+                    const int64_t x0 = r0 - P.pf_rows > 0 ? r0 - P.pf_rows : 0;
+                    const int64_t x1 = r1 + P.pf_rows < P.N ? r1 + P.pf_rows : P.N;
+                    const char* px = reinterpret_cast<const char*>(P.X + x0 * P.ldx);
+                    const int64_t nbx = (x1 - x0) * P.ldx * 4;
+                    for (int64_t o = (int64_t)lane * 128; o < nbx; o += 32 * 128)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(px + o));
                 }
             }
         }
     } else if (warp == 5) {
         // =================================================================== MMA issuer (one lane)
         if (lane == 0) {
-            const uint32_t idesc_main = make_idesc_tf32_mn(128, BN);
-            const uint32_t idesc_self = make_idesc_tf32_mn(128, P.BNS > 0 ? P.BNS : 16);
-            uint32_t it = 0, cc = 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            constexpr uint32_t idesc = make_idesc_tf32_mn(MROWS, NMMA);
+            if constexpr (RES) mbar_wait(wfull, 0);
+            uint32_t it = 0, tt = 0;
+            long long c_full = 0, c_tempty = 0;
+            const long long c_begin = clock64();
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
+                const uint32_t buf = tt & 1;
+                long long c0 = clock64();
+                mbar_wait(tempty + buf, ((tt >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                c_tempty += clock64() - c0;
+                tc_fence_after();
+                const uint32_t d_main = tmem_base + buf * 256;
+                const uint32_t d_gate = d_main + (16u << 16);          // second M = 64 accumulator, interleaved at lane 16
                 for (int kb = 0; kb < nkb_total; ++kb, ++it) {
-                    const bool is_self = kb >= nkb_chain;
-                    const bool chunk_start = is_self || (kb % P.chunk_kb) == 0;
-                    const bool chunk_end = is_self || (kb % P.chunk_kb) == P.chunk_kb - 1 || kb == nkb_chain - 1;
-                    const uint32_t buf = cc % NBUF;
-                    if (chunk_start) {
-                        mbar_wait(tempty + buf, ((cc / NBUF) & 1) ^ 1);    // epilogue has drained this accumulator
-                        tc_fence_after();
-                    }
-                    const int s = it % FL_STAGES;
-                    mbar_wait(full + s, (it / FL_STAGES) & 1);
+                    const uint32_t s = it % nstages;
+                    c0 = clock64();
+                    mbar_wait(full + s, (it / nstages) & 1);
+                    c_full += clock64() - c0;
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
-                    const uint64_t da_hi = make_kmajor_sw128_desc(sa);
-                    const uint64_t da_lo = make_kmajor_sw128_desc(sa + FL_PLANE);
-                    const uint64_t db_hi = make_kmajor_sw128_desc(sa + 2 * FL_PLANE);
-                    const uint64_t db_lo = make_kmajor_sw128_desc(sa + 2 * FL_PLANE + Cfg::B_BYTES);
-                    const uint32_t d = tmem_base + buf * BN;
-                    const uint32_t idesc = is_self ? idesc_self : idesc_main;
+                    const uint32_t sa = smem_u32(stages + (size_t)s * STAGE_BYTES);
+                    const uint64_t dh = make_kmajor_sw128_desc(sa);                 // N side: [H raw ; H lo]  (2 * ROWS rows)
+                    const uint64_t dw = make_kmajor_sw128_desc(RES ? smem_u32(wres + (size_t)kb * WPLANE) : sa + HP_BYTES);
+                    const bool gate = P.self_mode == 1 && kb == P.nkb_main;
+                    const uint32_t d = gate ? d_gate : d_main;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 8 TF32 = 32 bytes along K inside the swizzled row
-                        umma_tf32(d, da_lo + adv, db_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
-                        umma_tf32(d, da_hi + adv, db_lo + adv, idesc, 1u);
-                        umma_tf32(d, da_hi + adv, db_hi + adv, idesc, 1u);
+                        umma_tf32(d, dw + adv, dh + adv, idesc, ((gate || kb == 0) && k == 0) ? 0u : 1u);
                     }
                     umma_commit(empty + s);                                    // stage reusable once these MMAs retire
-                    if (chunk_end) {
-                        umma_commit(tfull + buf);                              // chunk complete -> epilogue
-                        ++cc;
-                    }
                 }
+                umma_commit(tfull + buf);                                      // tile complete -> epilogue
+            }
+            if (P.dbg) {
+                atomicAdd(P.dbg + 3, (unsigned long long)c_full);
+                atomicAdd(P.dbg + 4, (unsigned long long)c_tempty);
+                atomicAdd(P.dbg + 5, (unsigned long long)(clock64() - c_begin));
             }
         }
     } else if (warp < 4) {
-        // =================================================================== epilogue (4 warps, one TMEM lane quarter each)
-        const int quarter = warp & 3;
-        const int nchunks = (nkb_chain + P.chunk_kb - 1) / P.chunk_kb;
-        const bool live_quarter = quarter * 32 < ROWS;
+        // =================================================================== epilogue (128 threads)
+        // Accumulator D[m, n]: column n = tile row (n < ROWS: x H_hi, n >= ROWS: x H_lo); weight-plane row m sits in TMEM lane
+        //   BNH = 64 (M = 128): lane m;  rows 0-63 W_hi (output column m), 64-127 W_lo
+        //   BNH = 32 (M = 64) : lane (m % 16) + 32 * (m / 16);  rows 0-31 W_hi, 32-63 W_lo; the gate accumulator uses the
+        //                       same mapping 16 lanes higher.  So warp q sees in lanes 0-15 main rows 16q.., in 16-31 gate rows.
+        // Per chunk of 32 tile rows: every warp adds its H_hi and H_lo columns and transposes its lanes through shared memory
+        // (T[row][m], conflict-free); then thread (row r, group g) finishes 8 output columns of one row: hi-weight + lo-weight
+        // partial sums + bias, ReLU, two 128-bit stores; the gates of a row are spread over its 4 threads.
+        const int q = warp;
+        constexpr int TS = BNH == 32 ? 68 : 132;                       // row stride of T in floats
+        float* Tm = xch;
+        float* Tg = xch + 32 * 68 + 16;                                // gate rows (BNH = 32), shifted by 16 banks
         const int Fo = P.Nc, G = P.G;
-        uint32_t cc = 0;
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-            const int rloc = quarter * 32 + lane;
-            const int64_t row = (int64_t)tile * ROWS + rloc;
-            const bool live = live_quarter && rloc < ROWS && row < P.N;
-            float acc[BN];
+        const bool has_gates = BNH == 32 && P.self_mode == 1;
+        const int et = threadIdx.x;                                    // 0..127
+        const int fr = et >> 2, fg = et & 3;                           // finishing role: row of the chunk, column group
+        const bool vec_out = (P.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
+        uint32_t tt = 0;
+        long long c_tfull = 0;
+        const long long c_begin = clock64();
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
+            const uint32_t buf = tt & 1;
+            const long long cw = clock64();
+            mbar_wait(tfull + buf, (tt >> 1) & 1);
+            c_tfull += clock64() - cw;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+            const int64_t row0 = (int64_t)tile * ROWS;
+#pragma unroll 1
+            for (int c0 = 0; c0 < ROWS; c0 += 32) {
+                {
+                    float vh[32], vl[32];
+                    tmem_ld32(taddr + c0, vh);
+                    tmem_ld32(taddr + ROWS + c0, vl);
+                    float* dst;
+                    if constexpr (BNH == 32) dst = lane < 16 ? Tm + 16 * q + lane : Tg + 16 * q + (lane - 16);
+                    else dst = Tm + 32 * q + lane;
 #pragma unroll
-            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-            for (int ch = 0; ch < nchunks; ++ch, ++cc) {
-                const uint32_t buf = cc % NBUF;
-                mbar_wait(tfull + buf, (cc / NBUF) & 1);
-                tc_fence_after();
-                if (live_quarter) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
-#pragma unroll
-                    for (int j0 = 0; j0 < BN; j0 += 32) {
-                        float v[32];
-                        tmem_ld32(taddr + j0, v);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[j0 + i] += v[i];
-                    }
+                    for (int i = 0; i < 32; ++i) dst[i * TS] = vh[i] + vl[i];
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty + buf);
-            }
-            // ---- main columns: bias (+ ReLU) and row store
-            if (live) {
-                float* dst = P.out + row * P.ldo;
-                const bool vec = (P.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int64_t r = row0 + c0 + fr;
+                if (c0 + fr < ROWS && r < P.N) {
+                    const float* trow = Tm + fr * TS;
+                    float* orow = P.out + r * P.ldo;
 #pragma unroll
-                for (int j = 0; j < BN; j += 4) {
-                    float o[4];
+                    for (int gg = 0; gg < BNH / 32; ++gg) {
+                        const int f0 = 8 * (fg + 4 * gg);
+                        if (f0 < Fo) {
+                            float o[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float t = acc[j + i];
-                        if (P.bias && j + i < Fo) t += __ldg(P.bias + j + i);
-                        if (P.epi == 1) t = fmaxf(t, 0.f);
-                        o[i] = t;
+                            for (int h = 0; h < 2; ++h) {
+                                const float4 a = *reinterpret_cast<const float4*>(trow + f0 + 4 * h);
+                                const float4 b = *reinterpret_cast<const float4*>(trow + BNH + f0 + 4 * h);
+                                o[4 * h + 0] = a.x + b.x; o[4 * h + 1] = a.y + b.y; o[4 * h + 2] = a.z + b.z; o[4 * h + 3] = a.w + b.w;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                if (P.bias && f0 + k < Fo) o[k] += __ldg(P.bias + f0 + k);
+                                if (P.epi == 1) o[k] = fmaxf(o[k], 0.f);
+                            }
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                if (vec_out && f0 + 4 * h + 3 < Fo) {
+                                    *reinterpret_cast<float4*>(orow + f0 + 4 * h) = make_float4(o[4 * h], o[4 * h + 1], o[4 * h + 2], o[4 * h + 3]);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (f0 + 4 * h + k < Fo) orow[f0 + 4 * h + k] = o[4 * h + k];
+                                }
+                            }
+                        }
                     }
-                    if (vec && j + 3 < Fo) {
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (j + i < Fo) dst[j + i] = o[i];
-                    }
-                }
-            }
-            // ---- gate columns (own TMEM chunk): y[:, Fo + j] = tanh(p1_j) * tanh(p2_j); aux = [tanh(p1) | tanh(p2)]
-            if (P.self_mode == 1) {
-                const uint32_t buf = cc % NBUF;
-                mbar_wait(tfull + buf, (cc / NBUF) & 1);
-                tc_fence_after();
-                float v[32];
-                if (live_quarter) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
-                    tmem_ld32(taddr, v);       // BNS <= 32 <= BN columns of this buffer are meaningful
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty + buf);
-                ++cc;
-                if (live) {
-                    float* dst = P.out + row * P.ldo + Fo;
-                    float* ax = P.aux + row * P.ldaux;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j < G) {      // the self weight planes interleave the two gates: column 2j = p1_j, 2j+1 = p2_j
-                            float p1 = v[2 * j], p2 = v[2 * j + 1];
+                    if (has_gates) {
+                        const float* grow = Tg + fr * TS;          // gate rows interleave p1_j (2j) and p2_j (2j+1); lo rows 32 further
+                        float* ax = P.aux + r * P.ldaux;
+                        for (int j = fg; j < G; j += 4) {
+                            float p1 = grow[2 * j] + grow[32 + 2 * j], p2 = grow[2 * j + 1] + grow[32 + 2 * j + 1];
                             if (P.bias_s) {
                                 p1 += __ldg(P.bias_s + j);
                                 p2 += __ldg(P.bias_s + G + j);
                             }
-                            const float t1 = tanhf(p1), t2 = tanhf(p2);
-                            dst[j] = t1 * t2;
+                            const float t1 = tanh_fast(p1), t2 = tanh_fast(p2);
+                            orow[Fo + j] = t1 * t2;
                             ax[j] = t1;
                             ax[G + j] = t2;
                         }
                     }
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + buf);
+        }
+        if (P.dbg && lane == 0) {
+            atomicAdd(P.dbg + 6, (unsigned long long)c_tfull);
+            atomicAdd(P.dbg + 7, (unsigned long long)(clock64() - c_begin));
         }
     } else if (warp >= FL_CTRL_WARPS) {
         // =================================================================== aggregators
@@ -305,9 +356,14 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapBhi, const __grid_consta
         const int64_t ldx = P.ldx;
         const int Kstride = P.Kstride;
         uint32_t it = 0;
+        long long c_gather = 0, c_wait = 0;
+        const long long c_begin = clock64();
+        int tseq = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            if (aw == 0 && lane == 0) *reinterpret_cast<volatile int*>(agg_seq) = ++tseq;
             const int64_t row = (int64_t)tile * ROWS + rloc;
             int rs = 0, re = 0;
+            long long cg0 = clock64();
             if (row < P.N) {
                 rs = __ldg(rowptr + row);
                 re = __ldg(rowptr + row + 1);
@@ -322,13 +378,29 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapBhi, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
                     constexpr int U = 2;   // edges in flight per lane
+                    // the CSR slots of the NEXT iteration are fetched one iteration ahead, so that the index -> gather chain
+                    // costs one memory latency per iteration instead of two
+                    int sidx_n[U], eidx_n[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int p = max(min(rs + u, re - 1), 0);
+                        sidx_n[u] = rs < re ? __ldg(col + p) : 0;
+                        eidx_n[u] = (rs < re && eperm) ? __ldg(eperm + p) : p;
+                    }
                     for (int p0 = rs; p0 < re; p0 += U) {
                         int sidx[U], eidx[U];
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            const int p = min(p0 + u, re - 1);
-                            sidx[u] = __ldg(col + p);
-                            eidx[u] = eperm ? __ldg(eperm + p) : p;
+                            sidx[u] = sidx_n[u];
+                            eidx[u] = eidx_n[u];
+                        }
+                        if (p0 + U < re) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int p = min(p0 + U + u, re - 1);
+                                sidx_n[u] = __ldg(col + p);
+                                eidx_n[u] = eperm ? __ldg(eperm + p) : p;
+                            }
                         }
                         float w[U][KT];
                         float4 xa[U], xb[U];
@@ -357,17 +429,22 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapBhi, const __grid_consta
                         }
                     }
                     // hand the KT finished k-blocks to the tensor core
+                    __syncwarp();
+                    c_gather += clock64() - cg0;
 #pragma unroll
                     for (int k = 0; k < KT; ++k, ++it) {
-                        const int s = it % FL_STAGES;
-                        mbar_wait(empty + s, ((it / FL_STAGES) & 1) ^ 1);
-                        uint8_t* a_raw = smem + (size_t)s * Cfg::STAGE_BYTES;
-                        fl_store_chunk(a_raw, off0, &acc[k][0]);
-                        fl_store_chunk(a_raw, off1, &acc[k][4]);
+                        const uint32_t s = it % nstages;
+                        const long long cw = clock64();
+                        mbar_wait(empty + s, ((it / nstages) & 1) ^ 1);
+                        c_wait += clock64() - cw;
+                        uint8_t* a_raw = stages + (size_t)s * STAGE_BYTES;
+                        fl_store_chunk<ROWS * 128>(a_raw, off0, &acc[k][0]);
+                        fl_store_chunk<ROWS * 128>(a_raw, off1, &acc[k][4]);
                         fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full + s);
                     }
+                    cg0 = clock64();
                 }
             }
             if (P.self_mode != 0) {
@@ -385,59 +462,56 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapBhi, const __grid_consta
                         sv[4] = t.x; sv[5] = t.y; sv[6] = t.z; sv[7] = t.w;
                     }
                 }
-                const int s = it % FL_STAGES;
-                mbar_wait(empty + s, ((it / FL_STAGES) & 1) ^ 1);
-                uint8_t* a_raw = smem + (size_t)s * Cfg::STAGE_BYTES;
-                fl_store_chunk(a_raw, off0, &sv[0]);
-                fl_store_chunk(a_raw, off1, &sv[4]);
+                const uint32_t s = it % nstages;
+                mbar_wait(empty + s, ((it / nstages) & 1) ^ 1);
+                uint8_t* a_raw = stages + (size_t)s * STAGE_BYTES;
+                fl_store_chunk<ROWS * 128>(a_raw, off0, &sv[0]);
+                fl_store_chunk<ROWS * 128>(a_raw, off1, &sv[4]);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full + s);
                 ++it;
             }
         }
+        if (P.dbg && lane == 0) {
+            atomicAdd(P.dbg + 0, (unsigned long long)c_gather);
+            atomicAdd(P.dbg + 1, (unsigned long long)c_wait);
+            atomicAdd(P.dbg + 2, (unsigned long long)(clock64() - c_begin));
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
-// Pre-split (hi = RN TF32, lo = residual), transposed (K-major) weight planes, one [BN x 32] plane per k-block in the
-// order the aggregators produce them: kb = fh * K + k covers rows (k * F + fh * 32 + c), c < 32, of Bmain [K*F, Nc];
-// kb = nfh * K is the self block Bself [Fs, Nc] when it accumulates into the main columns (mode 2).  In mode 1 the
-// self block has its own [BNS x 32] plane pair (Bself [Fs, Ns = 2G], output columns interleaved p1_0 p2_0 p1_1 ..).
-__global__ void k_fl_prep_weights(const float* __restrict__ Bmain, int64_t ldb, int K, int F, int Nc, int nfh, int BN,
-                                  const float* __restrict__ Bself, int64_t ldbs, int Fs, int Ns, int self_mode, int BNS,
-                                  float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ shi,
-                                  float* __restrict__ slo) {
+// Pre-split, transposed (K-major) weight planes: one [2*BNH rows x 32] plane per k-block, in the order the aggregators
+// produce the k-blocks: kb = fh * K + k covers rows (k * F + fh * 32 + c), c < 32, of Bmain [K*F, Nc]; kb = nfh * K is
+// the self block.  Plane rows (the MMA's M side): [0, BNH) hi = RN-TF32(w) of output column n, [BNH, 2 BNH) lo = w - hi.
+// Self plane: mode 2 -> Bself [Fs, Nc] in the same layout; mode 1 -> the gate weights Bself [Fs, 2G] with the gate
+// columns interleaved (p1_0 p2_0 p1_1 p2_1 ..).
+__global__ void k_fl_prep_weights(const float* __restrict__ Bmain, int64_t ldb, int K, int F, int Nc, int nfh, int BNH,
+                                  const float* __restrict__ Bself, int64_t ldbs, int Fs, int Ns, int self_mode,
+                                  float* __restrict__ planes) {
     const int nkb_main = nfh * K;
-    const int nkb_chain = nkb_main + (self_mode == 2 ? 1 : 0);
-    const int total_main = nkb_chain * BN * 32;
-    const int total = total_main + (self_mode == 1 ? BNS * 32 : 0);
+    const int nkb_total = nkb_main + (self_mode != 0 ? 1 : 0);
+    const int MR = 2 * BNH;
+    const int total = nkb_total * MR * 32;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int kb = i / (MR * 32), m = (i / 32) % MR, c = i % 32;
+        const int n = m % BNH;
+        const bool is_lo = m >= BNH;
         float v = 0.f;
-        float *ph, *pl;
-        if (i < total_main) {
-            const int kb = i / (BN * 32), n = (i / 32) % BN, c = i % 32;
-            if (kb < nkb_main) {
-                const int fh = kb / K, k = kb % K, f = fh * 32 + c;
-                if (f < F && n < Nc) v = __ldg(Bmain + ((int64_t)k * F + f) * ldb + n);
-            } else if (c < Fs && n < Nc) {
-                v = __ldg(Bself + (int64_t)c * ldbs + n);
-            }
-            ph = hi + i;
-            pl = lo + i;
+        if (kb < nkb_main) {
+            const int fh = kb / K, k = kb % K, f = fh * 32 + c;
+            if (f < F && n < Nc) v = __ldg(Bmain + ((int64_t)k * F + f) * ldb + n);
+        } else if (self_mode == 2) {
+            if (c < Fs && n < Nc) v = __ldg(Bself + (int64_t)c * ldbs + n);
         } else {
-            const int j = i - total_main;
-            const int n = j / 32, c = j % 32;
-            const int src_n = (n & 1) ? (Ns / 2 + (n >> 1)) : (n >> 1);      // interleave [p1 | p2] -> p1_0 p2_0 p1_1 p2_1 ..
+            const int src_n = (n & 1) ? (Ns / 2 + (n >> 1)) : (n >> 1);
             if (c < Fs && n < Ns) v = __ldg(Bself + (int64_t)c * ldbs + src_n);
-            ph = shi + j;
-            pl = slo + j;
         }
         const float h = tf32_rn(v);
-        *ph = h;
-        *pl = v - h;
+        planes[i] = is_lo ? v - h : h;
     }
 }
 
@@ -445,12 +519,37 @@ __global__ void k_fl_prep_weights(const float* __restrict__ Bmain, int64_t ldb, 
 
 using namespace gnnml3;
 
-static inline int fl_bn_for(int Nc) { return Nc <= 32 ? 32 : 64; }
+static inline int fl_bnh_for(int Nc) { return Nc <= 32 ? 32 : 64; }
 static inline int fl_kt_for(int K) {
     if (K >= 4 && K <= 8) return K;
     if (K > 8 && K <= 16 && K % 2 == 0) return K / 2;
     return 0;
 }
+
+// optional cycle counters (GNNML3_FUSED_DEBUG=1): [0] aggregator gather, [1] aggregator waiting for a free stage,
+// [2] aggregator total, [3] MMA thread waiting for stages, [4] MMA thread waiting for a drained accumulator, [5] MMA
+// thread total, [6] epilogue waiting for a tile, [7] epilogue total (sums over warps / CTAs)
+static unsigned long long* g_fl_dbg = nullptr;
+static const bool g_fl_debug = [] {
+    const char* e = getenv("GNNML3_FUSED_DEBUG");
+    return e && e[0] == '1';
+}();
+
+extern "C" int gnnml3_fused_debug_counters(unsigned long long* out8_host, int reset) {
+    if (!g_fl_dbg) {
+        for (int i = 0; i < 8; ++i) out8_host[i] = 0;
+        return GNNML3_OK;
+    }
+    GNNML3_CUDA(cudaDeviceSynchronize());
+    GNNML3_CUDA(cudaMemcpy(out8_host, g_fl_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 8 * sizeof(unsigned long long)));
+    return GNNML3_OK;
+}
+
+static const int g_fl_pf_rows = [] {
+    const char* e = getenv("GNNML3_FUSED_PF_ROWS");
+    return e ? atoi(e) : 40;
+}();
 
 static int g_fl_nagg16 = [] {
     const char* e = getenv("GNNML3_FUSED_NAGG16");
@@ -459,48 +558,67 @@ static int g_fl_nagg16 = [] {
 
 extern "C" int gnnml3_fused_supported(int K, int Kstride, int F, int Nc, int Fs, int self_mode, int Ns) {
     const int kt = fl_kt_for(K);
-    if (kt == 0 || F < 1 || F > 256 || Nc < 1 || Nc > 64) return 0;
+    if (kt == 0 || F < 1 || Nc < 1 || Nc > 64) return 0;
+    if (((F + 31) / 32) * K > 24) return 0;               // accumulation chain per tile kept short (TMEM adds truncate)
     if (kt % 4 == 0 && Kstride % 4 != 0) return 0;        // 128-bit edge-weight loads
     if (kt % 4 != 0 && kt % 2 == 0 && Kstride % 2 != 0) return 0;
     if (self_mode != 0 && (Fs < 1 || Fs > 32)) return 0;
-    if (self_mode == 1 && (Ns < 1 || Ns > 32)) return 0;
+    if (self_mode == 1 && (Ns < 2 || Ns > 32 || Ns % 2 != 0 || Nc > 32)) return 0;
     return 1;
 }
 
 extern "C" size_t gnnml3_fused_workspace_bytes(int K, int F, int Nc, int self_mode) {
-    const int BN = fl_bn_for(Nc);
     const int nfh = cdiv(F, 32);
-    const size_t planes = (size_t)(nfh * K + (self_mode == 2 ? 1 : 0)) * BN * 32;
-    return align_up((2 * planes + 2 * 32 * 32) * sizeof(float), 256);
+    return align_up((size_t)(nfh * K + (self_mode != 0 ? 1 : 0)) * 2 * fl_bnh_for(Nc) * 128, 256);
 }
 
-template <int KT, int BN, int NAGG>
-static int fl_launch(const CUtensorMap& mBhi, const CUtensorMap& mBlo, const CUtensorMap& mShi, const CUtensorMap& mSlo,
-                     FLParams& P, cudaStream_t st) {
-    using Cfg = FLCfg<BN>;
-    static bool configured = false;
-    if (!configured) {
-        GNNML3_CUDA(cudaFuncSetAttribute(k_fused_agg_proj<KT, BN, NAGG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::SMEM));
-        configured = true;
+constexpr size_t FL_SMEM_MAX = 227 * 1024;                                              // opt-in limit per CTA on sm_100
+constexpr size_t FL_SMEM_FIXED = 2 * FL_XCH * sizeof(float) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+template <int KT, int BNH, int NAGG, bool RES>
+static int fl_launch2(const CUtensorMap& mW, FLParams& P, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (configured < smem) {
+        GNNML3_CUDA(cudaFuncSetAttribute(k_fused_agg_proj<KT, BNH, NAGG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FL_SMEM_MAX));
+        configured = FL_SMEM_MAX;
     }
-    constexpr int ROWS = 8 * NAGG;
-    P.n_tiles = cdiv(P.N, ROWS);
     const int grid = P.n_tiles < kNumSMs ? P.n_tiles : kNumSMs;
-    k_fused_agg_proj<KT, BN, NAGG><<<grid, 32 * (FL_CTRL_WARPS + NAGG), Cfg::SMEM, st>>>(mBhi, mBlo, mShi, mSlo, P);
+    k_fused_agg_proj<KT, BNH, NAGG, RES><<<grid, 32 * (FL_CTRL_WARPS + NAGG), smem, st>>>(mW, P);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
 
+// Weight planes stay resident in shared memory when at least 3 H-plane stages fit beside them; otherwise every k-block's
+// plane is streamed from L2 into its stage (large K * F: L2-bandwidth bound).
+template <int KT, int BNH, int NAGG>
+static int fl_launch(const CUtensorMap& mW, FLParams& P, cudaStream_t st) {
+    constexpr int ROWS = 8 * NAGG;
+    constexpr size_t HP = 2 * ROWS * 128, WPLANE = 2 * BNH * 128;
+    P.n_tiles = cdiv(P.N, ROWS);
+    const size_t nkb_total = P.nkb_main + (P.self_mode != 0 ? 1 : 0);
+    const size_t resident = nkb_total * WPLANE;
+    if (resident + 3 * HP + FL_SMEM_FIXED <= FL_SMEM_MAX) {
+        size_t ns = (FL_SMEM_MAX - FL_SMEM_FIXED - resident) / HP;
+        if (ns > FL_MAX_STAGES) ns = FL_MAX_STAGES;
+        P.nstages = (int)ns;
+        return fl_launch2<KT, BNH, NAGG, true>(mW, P, resident + ns * HP + FL_SMEM_FIXED, st);
+    }
+    size_t ns = (FL_SMEM_MAX - FL_SMEM_FIXED) / (HP + WPLANE);
+    if (ns > FL_MAX_STAGES) ns = FL_MAX_STAGES;
+    P.nstages = (int)ns;
+    return fl_launch2<KT, BNH, NAGG, false>(mW, P, ns * (HP + WPLANE) + FL_SMEM_FIXED, st);
+}
+
 // aggregator warps per CTA by register need: KT x 8 accumulators per lane.  512 threads leave 128 registers per thread
-// (KT >= 7), 640 threads 96 (KT <= 6); the experimental 16-warp / 4-supports-per-pass variant runs at 80.
+// (KT >= 7), 640 threads 96 (KT <= 6); the 16-warp / 4-supports-per-pass variant runs at 80.
 #define FL_DISPATCH_KT(KTV, BNV)                                                                      \
     switch (KTV) {                                                                                    \
-        case 4: return fl_launch<4, BNV, 14>(mBhi, mBlo, mShi, mSlo, P, st);                          \
-        case 5: return fl_launch<5, BNV, 14>(mBhi, mBlo, mShi, mSlo, P, st);                          \
-        case 6: return fl_launch<6, BNV, 14>(mBhi, mBlo, mShi, mSlo, P, st);                          \
-        case 7: return fl_launch<7, BNV, 10>(mBhi, mBlo, mShi, mSlo, P, st);                          \
-        case 8: return fl_launch<8, BNV, 10>(mBhi, mBlo, mShi, mSlo, P, st);                          \
+        case 4: return fl_launch<4, BNV, 14>(mW, P, st);                                              \
+        case 5: return fl_launch<5, BNV, 14>(mW, P, st);                                              \
+        case 6: return fl_launch<6, BNV, 14>(mW, P, st);                                              \
+        case 7: return fl_launch<7, BNV, 10>(mW, P, st);                                              \
+        case 8: return fl_launch<8, BNV, 10>(mW, P, st);                                              \
         default: return set_err(GNNML3_ERR_INVALID, "fused_agg_proj: no kernel for K tile %d", KTV);  \
     }
 
@@ -525,44 +643,36 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
     if (workspace_bytes < gnnml3_fused_workspace_bytes(K, F, Nc, self_mode))
         return set_err(GNNML3_ERR_WORKSPACE, "fused_agg_proj: workspace too small");
     cudaStream_t st = (cudaStream_t)stream_;
-    const int BN = fl_bn_for(Nc);
+    const int BNH = fl_bnh_for(Nc);
     const int KT = fl_kt_for(K);
     const int nfh = cdiv(F, 32);
     const int nkb_main = nfh * K;
-    const int nkb_chain = nkb_main + (self_mode == 2 ? 1 : 0);
-    const int BNS = self_mode == 1 ? (Ns <= 16 ? 16 : 32) : 0;
-    float* hi = (float*)workspace;
-    float* lo = hi + (size_t)nkb_chain * BN * 32;
-    float* shi = lo + (size_t)nkb_chain * BN * 32;
-    float* slo = shi + 32 * 32;
+    const int nkb_total = nkb_main + (self_mode != 0 ? 1 : 0);
+    float* planes = (float*)workspace;
     {
-        const int total = nkb_chain * BN * 32 + BNS * 32;
+        const int total = nkb_total * 2 * BNH * 32;
         const int blocks = cdiv(total, 256) > 592 ? 592 : cdiv(total, 256);
-        k_fl_prep_weights<<<blocks, 256, 0, st>>>(Bmain, ldb, K, F, Nc, nfh, BN, Bself, ldbs, Fs, Ns, self_mode, BNS, hi, lo,
-                                                  shi, slo);
+        k_fl_prep_weights<<<blocks, 256, 0, st>>>(Bmain, ldb, K, F, Nc, nfh, BNH, Bself, ldbs, Fs, Ns, self_mode, planes);
         GNNML3_LAUNCH_CHECK();
     }
-    CUtensorMap mBhi, mBlo, mShi, mSlo;
+    CUtensorMap mW;
     int rc;
-    if ((rc = make_map(&mBhi, hi, (int64_t)nkb_chain * BN, 32, 32, BN))) return rc;
-    if ((rc = make_map(&mBlo, lo, (int64_t)nkb_chain * BN, 32, 32, BN))) return rc;
-    if (self_mode == 1) {
-        if ((rc = make_map(&mShi, shi, BNS, 32, 32, BNS))) return rc;
-        if ((rc = make_map(&mSlo, slo, BNS, 32, 32, BNS))) return rc;
-    } else {
-        mShi = mBhi;
-        mSlo = mBlo;
-    }
+    if ((rc = make_map(&mW, planes, (int64_t)nkb_total * 2 * BNH, 32, 32, 2 * BNH))) return rc;
     FLParams P;
     P.rowptr = rowptr; P.col = col; P.eperm = eperm; P.ea = ea; P.Kstride = Kstride; P.K = K;
-    P.X = X; P.ldx = ldx; P.F = F; P.S = S; P.lds = lds; P.Fs = Fs; P.self_mode = self_mode; P.BNS = BNS;
-    P.N = N; P.n_tiles = 0; P.nfh = nfh; P.nkb_main = nkb_main; P.chunk_kb = 4;
+    P.X = X; P.ldx = ldx; P.F = F; P.S = S; P.lds = lds; P.Fs = Fs; P.self_mode = self_mode;
+    P.N = N; P.n_tiles = 0; P.nfh = nfh; P.nkb_main = nkb_main; P.nstages = 0; P.pf_rows = g_fl_pf_rows;
     P.bias = bias; P.bias_s = bias_s; P.out = out; P.ldo = ldo; P.Nc = Nc; P.aux = aux; P.ldaux = ldaux; P.G = G;
     P.epi = epilogue;
-    if (g_fl_nagg16 && K % 4 == 0 && Kstride % 4 == 0) {     // experiment: 16 aggregator warps, 4 supports per pass
-        if (BN == 32) return fl_launch<4, 32, 16>(mBhi, mBlo, mShi, mSlo, P, st);
-        return fl_launch<4, 64, 16>(mBhi, mBlo, mShi, mSlo, P, st);
+    if (g_fl_debug && !g_fl_dbg) {
+        GNNML3_CUDA(cudaMalloc(&g_fl_dbg, 8 * sizeof(unsigned long long)));
+        GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 8 * sizeof(unsigned long long)));
     }
-    if (BN == 32) { FL_DISPATCH_KT(KT, 32) }
+    P.dbg = g_fl_dbg;
+    if (g_fl_nagg16 && K % 4 == 0 && Kstride % 4 == 0) {     // experiment: 16 aggregator warps, 4 supports per pass
+        if (BNH == 32) return fl_launch<4, 32, 16>(mW, P, st);
+        return fl_launch<4, 64, 16>(mW, P, st);
+    }
+    if (BNH == 32) { FL_DISPATCH_KT(KT, 32) }
     FL_DISPATCH_KT(KT, 64)
 }

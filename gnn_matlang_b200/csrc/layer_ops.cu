@@ -97,57 +97,69 @@ k_ml3_act_bwd(const float* __restrict__ pre, int64_t ldp, const float* __restric
 // dx kernel gathers from: conv gradient in columns [0, Fo), zero padding to Fo4 = ceil4(Fo), gate gradients
 // [g1 | g2] in [Fo4, Fo4 + 2G), zero padding up to the row stride ldg (all 16-byte aligned blocks).  colpart as above,
 // in the logical order [conv | g1 | g2].
+constexpr int ACTY_ROWS = 128;      // rows per block; one thread per (row, 4-column group): 128-bit loads and stores
+constexpr int ACTY_MAXLD = 72;      // widest gpre row staged in shared memory for the column sums
 __global__ void __launch_bounds__(256)
 k_ml3_act_bwd_y(const float* __restrict__ y, int64_t ldy, const float* __restrict__ aux, int64_t ldaux,
                 const float* __restrict__ gy, int64_t ldgy, int64_t N, int Fo, int G, float* __restrict__ gpre, int64_t ldg,
-                float* __restrict__ colpart) {
-    __shared__ float red[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+                float* __restrict__ colpart, int vec_in) {
+    __shared__ __align__(16) float tile[ACTY_ROWS * ACTY_MAXLD];
     const int Fo4 = (Fo + 3) / 4 * 4, W2 = Fo + 2 * G;
-    const int64_t r0 = (int64_t)blockIdx.x * ACT_ROWS;
-    const int64_t r1 = min(N, r0 + ACT_ROWS);
-    for (int c0 = 0; c0 < (int)ldg; c0 += 32) {
-        const int c = c0 + tx;
-        int kind = 3, j = 0;                    // 0 conv, 1 gate 1, 2 gate 2, 3 padding
-        if (c < Fo) kind = 0;
-        else if (c >= Fo4 && c < Fo4 + G) { kind = 1; j = c - Fo4; }
-        else if (c >= Fo4 + G && c < Fo4 + 2 * G) { kind = 2; j = c - Fo4 - G; }
-        float s = 0.f;
-        if (c < (int)ldg) {
-            for (int64_t n = r0 + ty; n < r1; n += 8) {
-                float v = 0.f;
-                if (kind == 0) {
-                    v = __ldg(y + n * ldy + c) > 0.f ? __ldg(gy + n * ldgy + c) : 0.f;
-                } else if (kind != 3) {
+    const int ngroups = (int)(ldg / 4);
+    const int64_t r0 = (int64_t)blockIdx.x * ACTY_ROWS;
+    const int rows = (int)min((int64_t)ACTY_ROWS, N - r0);
+    for (int i = threadIdx.x; i < rows * ngroups; i += blockDim.x) {
+        const int rl = i / ngroups, cg = i - rl * ngroups, c = 4 * cg;
+        const int64_t n = r0 + rl;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c + 3 < Fo && vec_in) {
+            const float4 yy = ldg4(y + n * ldy + c), gg = ldg4(gy + n * ldgy + c);
+            v[0] = yy.x > 0.f ? gg.x : 0.f; v[1] = yy.y > 0.f ? gg.y : 0.f;
+            v[2] = yy.z > 0.f ? gg.z : 0.f; v[3] = yy.w > 0.f ? gg.w : 0.f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cc = c + k;
+                if (cc < Fo) {
+                    v[k] = __ldg(y + n * ldy + cc) > 0.f ? __ldg(gy + n * ldgy + cc) : 0.f;
+                } else if (cc >= Fo4 && cc < Fo4 + 2 * G) {
+                    const int j = (cc - Fo4) % G, second = (cc - Fo4) / G;
                     const float g = __ldg(gy + n * ldgy + Fo + j);
                     const float t1 = __ldg(aux + n * ldaux + j), t2 = __ldg(aux + n * ldaux + G + j);
-                    v = kind == 1 ? g * t2 * (1.f - t1 * t1) : g * t1 * (1.f - t2 * t2);
+                    v[k] = second ? g * t1 * (1.f - t2 * t2) : g * t2 * (1.f - t1 * t1);
                 }
-                gpre[n * ldg + c] = v;
-                s += v;
             }
         }
-        if (colpart) {
-            red[ty][tx] = s;
-            __syncthreads();
-            if (ty == 0 && kind != 3) {
-                float v = 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v += red[q][tx];
-                const int lc = kind == 0 ? c : (kind == 1 ? Fo + j : Fo + G + j);
-                colpart[(int64_t)blockIdx.x * W2 + lc] = v;
+        const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(gpre + n * ldg + c) = o;
+        if (colpart) *reinterpret_cast<float4*>(tile + rl * (int)ldg + c) = o;
+    }
+    if (colpart) {
+        __syncthreads();
+        const int c = threadIdx.x;
+        if (c < (int)ldg) {
+            int lc = -1;
+            if (c < Fo) lc = c;
+            else if (c >= Fo4 && c < Fo4 + 2 * G) lc = Fo + (c - Fo4);
+            if (lc >= 0) {
+                float t = 0.f;
+                for (int rl = 0; rl < rows; ++rl) t += tile[rl * (int)ldg + c];      // fixed order: deterministic
+                colpart[(int64_t)blockIdx.x * W2 + lc] = t;
             }
-            __syncthreads();
         }
     }
 }
 
+// out[c] = sum_b part[b][c]: one warp per column, lanes stride over the blocks, fixed-order shuffle tree (deterministic)
 __global__ void k_colsum_finish(const float* __restrict__ part, int nblocks, int W2, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= W2) return;
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * W2 + c];
-    out[c] = s;
+    for (int b = lane; b < nblocks; b += 32) s += part[(int64_t)b * W2 + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = s;
 }
 
 // one warp per (graph, 32-feature chunk)
@@ -225,7 +237,7 @@ extern "C" int gnnml3_ml3_act_bwd(const float* pre, int64_t ldp, const float* gy
     k_ml3_act_bwd<<<nb, 256, 0, st>>>(pre, ldp, gy, ldy, N, Fo, G, gpre, ldg, gate_out, ldgate, part);
     GNNML3_LAUNCH_CHECK();
     if (colsum) {
-        k_colsum_finish<<<cdiv(Fo + 2 * G, 128), 128, 0, st>>>(part, nb, Fo + 2 * G, colsum);
+        k_colsum_finish<<<cdiv(Fo + 2 * G, 8), 256, 0, st>>>(part, nb, Fo + 2 * G, colsum);
         GNNML3_LAUNCH_CHECK();
     }
     return GNNML3_OK;
@@ -263,7 +275,7 @@ extern "C" int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* au
         return GNNML3_OK;
     }
     const int Fo4 = (Fo + 3) / 4 * 4;
-    GNNML3_REQUIRE(y && gy && gpre && ldy >= Fo && ldgy >= Fo + G && ldg >= Fo4 + 2 * G && ldg <= 4096,
+    GNNML3_REQUIRE(y && gy && gpre && ldy >= Fo && ldgy >= Fo + G && ldg >= Fo4 + 2 * G && ldg <= ACTY_MAXLD,
                    "ml3_act_bwd_y: bad arguments");
     GNNML3_REQUIRE(G == 0 || (aux && ldaux >= 2 * G), "ml3_act_bwd_y: aux [N, 2G] required");
     float* part = nullptr;
@@ -273,11 +285,13 @@ extern "C" int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* au
             return set_err(GNNML3_ERR_WORKSPACE, "ml3_act_bwd_y: workspace too small");
         part = (float*)workspace;
     }
-    const int nb = cdiv(N, ACT_ROWS);
-    k_ml3_act_bwd_y<<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part);
+    GNNML3_REQUIRE(ldg % 4 == 0 && (uintptr_t)gpre % 16 == 0, "ml3_act_bwd_y: gpre rows must be 16-byte aligned");
+    const int nb = cdiv(N, ACTY_ROWS);
+    const int vec_in = (ldy % 4 == 0 && ldgy % 4 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)gy % 16 == 0) ? 1 : 0;
+    k_ml3_act_bwd_y<<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, vec_in);
     GNNML3_LAUNCH_CHECK();
     if (colsum) {
-        k_colsum_finish<<<cdiv(Fo + 2 * G, 128), 128, 0, st>>>(part, nb, Fo + 2 * G, colsum);
+        k_colsum_finish<<<cdiv(Fo + 2 * G, 8), 256, 0, st>>>(part, nb, Fo + 2 * G, colsum);
         GNNML3_LAUNCH_CHECK();
     }
     return GNNML3_OK;
