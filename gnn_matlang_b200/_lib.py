@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgnnml3_b200.so")
+LIB_PATH = os.environ.get("GNNML3_LIB", os.path.join(_HERE, "libgnnml3_b200.so"))   # override: experiments only
 
 _p = ctypes.c_void_p
 _i64 = ctypes.c_int64
