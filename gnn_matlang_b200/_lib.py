@@ -50,6 +50,9 @@ SIGNATURES = {
     "gnnml3_fused_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "gnnml3_fused_agg_proj": (_i, [_p, _p, _p, _p, _i, _i, _p, _i64, _i, _p, _i64, _i, _i, _p, _i64, _p, _i64, _i, _p, _p,
                                    _i64, _i, _p, _i64, _p, _i64, _i, _i, _p, _sz, _p]),
+    "gnnml3_fused_sddmm_supported": (_i, [_i, _i, _i]),
+    "gnnml3_fused_sddmm_workspace_bytes": (_sz, [_i]),
+    "gnnml3_fused_sddmm": (_i, [_p, _p, _p, _i64, _i, _p, _i64, _i, _p, _i, _i64, _p, _p, _sz, _p]),
     "gnnml3_segment_pool_fwd": (_i, [_p, _i64, _p, _i, _i, _i, _p, _p]),
     "gnnml3_segment_pool_bwd": (_i, [_p, _p, _i, _i, _i, _p, _i64, _p]),
     "gnnml3_spectral_max_nodes": (_i, [_i]),

@@ -1,0 +1,342 @@
+// Fused edge-feature gradient of SpectConv on Blackwell tensor cores:
+//     d ea[e, k] = < x[src_e, :],  (grad_out[dst_e, :] W_k^T) >            (reference: autograd through
+//     libs/spect_conv.py:76-80 -- the gradient of  sum_k scatter_add(ea[:, k] * x[src]) W_k  w.r.t. edge_attr)
+// The two-kernel path first materialises dH = grad_out [W_0^T .. W_{K-1}^T]  ([N, K*Fi], a GEMM) in HBM and then runs an
+// SDDMM over the CSR that reads it back.  Here a persistent CTA owns a tile of 64 dst rows:
+//   * the tile's rows of grad_out (conv columns of d pre) are written as raw + residual TF32 planes; one thread issues
+//     tcgen05.mma with the weights on the M side -- plane p holds rows [hi ; lo] of the 64 (k, i) pairs 64p .. 64p+63
+//     of Wr[(k,i), o] = W[k, i, o], resident in shared memory -- and the tile rows on the N side ([hi | lo], N = 128):
+//     16 instructions per tile produce all four 3xTF32 partial products of the whole dH tile in tensor memory;
+//   * epilogue warps add the partial products and transpose dH[(k,i), t] -> dH[t][(k,i)] into shared memory;
+//   * SDDMM warps (4 lanes per row) keep the row's K x 8 slice of dH in registers, gather each source row once per edge
+//     with 128-bit loads and reduce-scatter the K dot products over the row's lanes (no atomics, fixed order).
+// dH never touches HBM.  Supported: K * 32 <= 256 (K <= 8), Fi <= 32, Fo <= 32 -- every GNNML3 layer of the ZINC
+// configuration; other shapes keep the two-kernel path (gnnml3_gemm_nn + gnnml3_sddmm_k).
+#include "tc_common.cuh"
+
+namespace gnnml3 {
+
+constexpr int SD_ROWS = 64;                    // dst rows per tile
+constexpr int SD_NW = 8;                       // SDDMM warps (8 rows each)
+constexpr int SD_CTRL = 6;                     // warps 0-3 epilogue | 4 TMA | 5 MMA
+constexpr int SD_THREADS = 32 * (SD_CTRL + SD_NW);
+constexpr int SD_WPLANE = 128 * 128;           // one weight plane: 64 hi + 64 lo rows x 32 FP32
+constexpr int SD_GPLANES = 2 * SD_ROWS * 128;  // raw + lo plane of the grad_out tile
+constexpr int SD_LD = 260;                     // row stride (floats) of the dH tile in shared memory
+constexpr size_t SD_SMEM = 4 * SD_WPLANE + SD_GPLANES + 2 * (size_t)SD_ROWS * SD_LD * 4 + 1024 + 256;
+
+struct SDParams {
+    const int* rowptr;
+    const int* col;
+    const float* X;        // [N, Fi] gather source
+    int64_t ldx;
+    int Fi;
+    const float* GC;       // [N, Fo] grad_out (conv columns of d pre), 16-byte aligned rows
+    int64_t ldg;
+    int Fo;
+    int K;
+    int64_t N;
+    int n_tiles;
+    float* dea;            // [E, K] in CSR slot order
+};
+
+__device__ __forceinline__ float sd_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+template <int K>
+__global__ void __launch_bounds__(SD_THREADS, 1)
+k_fused_sddmm(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ SDParams P) {
+    constexpr int NP = (K * 32 + 63) / 64;           // weight planes / TMEM accumulators (<= 4)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* wres = smem;                                             // [4][SD_WPLANE]
+    uint8_t* gpl = smem + 4 * SD_WPLANE;                              // grad_out planes: raw [64 x 128 B] | lo
+    float* dhs = reinterpret_cast<float*>(gpl + SD_GPLANES);          // [2][SD_ROWS][SD_LD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dhs + 2 * SD_ROWS * SD_LD);
+    uint64_t* wfull = bars;          // weights landed
+    uint64_t* gfull = bars + 1;      // grad_out planes written        (SD_NW arrivals)   -> MMA
+    uint64_t* gempty = bars + 2;     // ... consumed                   (MMA commit)       -> SDDMM warps
+    uint64_t* tfull = bars + 3;      // dH tile complete in TMEM       (MMA commit)       -> epilogue
+    uint64_t* tempty = bars + 4;     // TMEM drained                   (4 arrivals)       -> MMA
+    uint64_t* hfull = bars + 5;      // [2] dH tile in shared memory   (4 arrivals)       -> SDDMM warps
+    uint64_t* hempty = bars + 7;     // [2] ... consumed               (SD_NW arrivals)   -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(wfull, 1);
+        mbar_init(gfull, SD_NW);
+        mbar_init(gempty, 1);
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(hfull + b, 4);
+            mbar_init(hempty + b, SD_NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wfull, NP * SD_WPLANE);
+            for (int p = 0; p < NP; ++p) tma_load_2d(wres + (size_t)p * SD_WPLANE, &mapW, wfull, 0, p * 128);
+        }
+    } else if (warp == 5) {
+        // =================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32_mn(128, 2 * SD_ROWS);
+            mbar_wait(wfull, 0);
+            uint32_t tt = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
+                mbar_wait(gfull, tt & 1);
+                mbar_wait(tempty, (tt & 1) ^ 1);
+                tc_fence_after();
+                const uint64_t dg = make_kmajor_sw128_desc(smem_u32(gpl));               // N side: [gc raw ; gc lo] rows
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const uint64_t dw = make_kmajor_sw128_desc(smem_u32(wres + (size_t)p * SD_WPLANE));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        umma_tf32(tmem_base + p * 128, dw + adv, dg + adv, idesc, k == 0 ? 0u : 1u);
+                    }
+                }
+                umma_commit(gempty);
+                umma_commit(tfull);
+            }
+        }
+    } else if (warp < 4) {
+        // =================================================================== epilogue: TMEM -> dH[t][(k,i)] in shared memory
+        // accumulator p: lane m = plane row (0-63: hi rows of (k,i) = 64p + m; 64-127: lo rows), column n = tile row
+        // (n < 64: x gc_hi, n >= 64: x gc_lo).  Warps 0,1 store hi-row sums, then warps 2,3 add the lo-row sums.
+        const int q = warp;
+        uint32_t tt = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
+            const uint32_t hb = tt & 1;
+            mbar_wait(tfull, tt & 1);
+            mbar_wait(hempty + hb, ((tt >> 1) & 1) ^ 1);
+            tc_fence_after();
+            float* dh = dhs + (size_t)hb * SD_ROWS * SD_LD;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int phase = 0; phase < 2; ++phase) {
+                if ((q >> 1) == phase) {
+#pragma unroll 1
+                    for (int p = 0; p < NP; ++p) {
+                        float* dcol = dh + 64 * p + 32 * (q & 1) + lane;
+#pragma unroll 1
+                        for (int t0 = 0; t0 < SD_ROWS; t0 += 16) {
+                            float vh[16], vl[16];
+                            tmem_ld16(taddr + p * 128 + t0, vh);
+                            tmem_ld16(taddr + p * 128 + SD_ROWS + t0, vl);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                float v = vh[i] + vl[i];
+                                if (phase == 1) v += dcol[(t0 + i) * SD_LD];
+                                dcol[(t0 + i) * SD_LD] = v;
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(tempty);
+                mbar_arrive(hfull + hb);
+            }
+        }
+    } else {
+        // =================================================================== SDDMM warps: 8 rows per warp, 4 lanes per row
+        const int aw = warp - SD_CTRL;
+        const int qd = lane >> 2, g = lane & 3;
+        const int rq = (qd >> 1) | ((qd & 1) << 2);            // conflict-free plane stores (see fused_layer.cu)
+        const int rloc = aw * 8 + rq;
+        const uint32_t row_off = (uint32_t)aw * 1024u + (uint32_t)rq * 128u;
+        const uint32_t off0 = row_off + (uint32_t)((g ^ rq) << 4);
+        const uint32_t off1 = row_off + (uint32_t)(((g + 4) ^ rq) << 4);
+        // where this lane's fully reduced values land after the reduce-scatter over the quad: 2 channels per lane
+        constexpr int KP = 8;
+        auto write_gc = [&](int tile, uint32_t seq) {
+            const int64_t row = (int64_t)tile * SD_ROWS + rloc;
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = 0.f;
+            if (row < P.N) {
+                const float* gr = P.GC + row * P.ldg;
+                if (g * 4 < P.Fo) {
+                    const float4 t = ldg4(gr + g * 4);
+                    a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+                }
+                if (16 + g * 4 < P.Fo) {
+                    const float4 t = ldg4(gr + 16 + g * 4);
+                    a[4] = t.x; a[5] = t.y; a[6] = t.z; a[7] = t.w;
+                }
+            }
+            mbar_wait(gempty, (seq & 1) ^ 1);
+            *reinterpret_cast<float4*>(gpl + off0) = make_float4(a[0], a[1], a[2], a[3]);
+            *reinterpret_cast<float4*>(gpl + off1) = make_float4(a[4], a[5], a[6], a[7]);
+            *reinterpret_cast<float4*>(gpl + SD_ROWS * 128 + off0) = make_float4(sd_lo(a[0]), sd_lo(a[1]), sd_lo(a[2]), sd_lo(a[3]));
+            *reinterpret_cast<float4*>(gpl + SD_ROWS * 128 + off1) = make_float4(sd_lo(a[4]), sd_lo(a[5]), sd_lo(a[6]), sd_lo(a[7]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gfull);
+        };
+        uint32_t tt = 0;
+        if ((int)blockIdx.x < P.n_tiles) write_gc(blockIdx.x, 0);
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
+            if (tile + (int)gridDim.x < P.n_tiles) write_gc(tile + gridDim.x, tt + 1);      // next tile's planes -> MMA runs ahead
+            const uint32_t hb = tt & 1;
+            const int64_t row = (int64_t)tile * SD_ROWS + rloc;
+            int rs = 0, cnt = 0;
+            if (row < P.N) {
+                rs = __ldg(P.rowptr + row);
+                cnt = __ldg(P.rowptr + row + 1) - rs;
+            }
+            int maxcnt = cnt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
+            mbar_wait(hfull + hb, (tt >> 1) & 1);
+            // the row's slice of dH: channels k = 0..K-1, features 8g .. 8g+7
+            const float* dh = dhs + (size_t)hb * SD_ROWS * SD_LD + (size_t)rloc * SD_LD + 8 * g;
+            float gv[K][8];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(dh + 32 * k);
+                const float4 b = *reinterpret_cast<const float4*>(dh + 32 * k + 4);
+                gv[k][0] = a.x; gv[k][1] = a.y; gv[k][2] = a.z; gv[k][3] = a.w;
+                gv[k][4] = b.x; gv[k][5] = b.y; gv[k][6] = b.z; gv[k][7] = b.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hempty + hb);          // dH slice is in registers: the buffer may be refilled
+            const bool v0 = 8 * g < P.Fi, v1 = 8 * g + 4 < P.Fi;
+            for (int i = 0; i < maxcnt; ++i) {
+                const bool act = i < cnt;
+                float part[KP];
+#pragma unroll
+                for (int k = 0; k < KP; ++k) part[k] = 0.f;
+                const int p = rs + i;
+                if (act) {
+                    const int s = __ldg(P.col + p);
+                    const float* xr = P.X + (int64_t)s * P.ldx + 8 * g;
+                    const float4 xa = v0 ? ldg4(xr) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 xb = v1 ? ldg4(xr + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        float t = gv[k][0] * xa.x;
+                        t = fmaf(gv[k][1], xa.y, t);
+                        t = fmaf(gv[k][2], xa.z, t);
+                        t = fmaf(gv[k][3], xa.w, t);
+                        t = fmaf(gv[k][4], xb.x, t);
+                        t = fmaf(gv[k][5], xb.y, t);
+                        t = fmaf(gv[k][6], xb.z, t);
+                        t = fmaf(gv[k][7], xb.w, t);
+                        part[k] = t;
+                    }
+                }
+                // reduce-scatter over the 4 lanes of the row: 8 -> 4 -> 2 values per lane
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const bool upper = (g & 2) != 0;
+                    const float keep = upper ? part[q4 + 4] : part[q4];
+                    const float send = upper ? part[q4] : part[q4 + 4];
+                    part[q4] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+#pragma unroll
+                for (int q2 = 0; q2 < 2; ++q2) {
+                    const bool upper = (g & 1) != 0;
+                    const float keep = upper ? part[q2 + 2] : part[q2];
+                    const float send = upper ? part[q2] : part[q2 + 2];
+                    part[q2] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                }
+                // lane g now owns channels kbase, kbase + 1 with kbase = 4 * (g >> 1) + 2 * (g & 1)
+                if (act) {
+                    const int kbase = 4 * (g >> 1) + 2 * (g & 1);
+                    float* o = P.dea + (int64_t)p * K + kbase;
+                    if (kbase + 1 < K) {
+                        *reinterpret_cast<float2*>(o) = make_float2(part[0], part[1]);
+                    } else if (kbase < K) {
+                        o[0] = part[0];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// Weight planes: plane p, row r < 64: hi of Wr[(k, i) = 64p + r][o] = W[k, i, o] (i < Fi, o < Fo, zero padded), rows 64..127 lo
+__global__ void k_sd_prep_weights(const float* __restrict__ W, int K, int Fi, int Fo, float* __restrict__ planes) {
+    const int np = (K * 32 + 63) / 64;
+    const int total = np * 128 * 32;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int p = idx / (128 * 32), m = (idx / 32) % 128, o = idx % 32;
+        const int ki = 64 * p + (m % 64), k = ki / 32, i = ki % 32;
+        float v = 0.f;
+        if (k < K && i < Fi && o < Fo) v = __ldg(W + ((int64_t)k * Fi + i) * Fo + o);
+        const float h = tf32_rn(v);
+        planes[idx] = m >= 64 ? v - h : h;
+    }
+}
+
+}  // namespace gnnml3
+
+using namespace gnnml3;
+
+extern "C" int gnnml3_fused_sddmm_supported(int K, int Fi, int Fo) {
+    return (K >= 2 && K <= 8 && K % 2 == 0 && Fi >= 1 && Fi <= 32 && Fo >= 1 && Fo <= 32) ? 1 : 0;
+}
+
+extern "C" size_t gnnml3_fused_sddmm_workspace_bytes(int K) { return align_up((size_t)4 * SD_WPLANE, 256); }
+
+template <int K>
+static int sd_launch(const CUtensorMap& mW, SDParams& P, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        GNNML3_CUDA(cudaFuncSetAttribute(k_fused_sddmm<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM));
+        configured = true;
+    }
+    const int grid = P.n_tiles < kNumSMs ? P.n_tiles : kNumSMs;
+    k_fused_sddmm<K><<<grid, SD_THREADS, SD_SMEM, st>>>(mW, P);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+extern "C" int gnnml3_fused_sddmm(const int32_t* rowptr, const int32_t* col, const float* X, int64_t ldx, int Fi, const float* GC,
+                                  int64_t ldg, int Fo, const float* W, int K, int64_t N, float* dea, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+    GNNML3_REQUIRE(N > 0 && N < (1ll << 31) - 256, "fused_sddmm: bad N");
+    GNNML3_REQUIRE(rowptr && col && X && GC && W && dea && workspace, "fused_sddmm: NULL pointer");
+    GNNML3_REQUIRE(gnnml3_fused_sddmm_supported(K, Fi, Fo), "fused_sddmm: unsupported shape K=%d Fi=%d Fo=%d", K, Fi, Fo);
+    GNNML3_REQUIRE(ldx % 4 == 0 && (uintptr_t)X % 16 == 0 && ldg % 4 == 0 && (uintptr_t)GC % 16 == 0,
+                   "fused_sddmm: X and GC rows must be 16-byte aligned");
+    GNNML3_REQUIRE((uintptr_t)dea % 8 == 0, "fused_sddmm: dea must be 8-byte aligned");
+    if (workspace_bytes < gnnml3_fused_sddmm_workspace_bytes(K)) return set_err(GNNML3_ERR_WORKSPACE, "fused_sddmm: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream_;
+    float* planes = (float*)workspace;
+    k_sd_prep_weights<<<64, 256, 0, st>>>(W, K, Fi, Fo, planes);
+    GNNML3_LAUNCH_CHECK();
+    const int np = (K * 32 + 63) / 64;
+    CUtensorMap mW;
+    int rc;
+    if ((rc = make_map(&mW, planes, (int64_t)np * 128, 32, 32, 128))) return rc;
+    SDParams P;
+    P.rowptr = rowptr; P.col = col; P.X = X; P.ldx = ldx; P.Fi = Fi; P.GC = GC; P.ldg = ldg; P.Fo = Fo; P.K = K; P.N = N;
+    P.n_tiles = cdiv(N, SD_ROWS);
+    P.dea = dea;
+    switch (K) {
+        case 2: return sd_launch<2>(mW, P, st);
+        case 4: return sd_launch<4>(mW, P, st);
+        case 6: return sd_launch<6>(mW, P, st);
+        case 8: return sd_launch<8>(mW, P, st);
+        default: return set_err(GNNML3_ERR_INVALID, "fused_sddmm: no kernel for K=%d", K);
+    }
+}

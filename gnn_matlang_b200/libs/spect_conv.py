@@ -280,6 +280,9 @@ class _ML3LayerFn(torch.autograd.Function):
         if ctx.fused_edge or need[1]:
             if plan.E == 0:
                 dea2 = torch.zeros_like(ea2)
+            elif ctx.fused and ops.fused_sddmm_supported(K, Fi, Fo):
+                # dH = gc [W_0^T ..] tile by tile in tensor memory / shared memory, consumed in place by the SDDMM
+                dea2 = ops.fused_sddmm(plan.rowptr, plan.col, x, gc, wconv, plan.E)
             else:
                 wp = wconv.permute(2, 0, 1).reshape(Fo, K * Fi).contiguous()
                 dH = ops.gemm_nn(gc, wp, precision=prec)

@@ -356,6 +356,26 @@ def ml3_act_bwd_y(y, aux, gy, Fo, G):
     return gpre, csum
 
 
+def fused_sddmm_supported(K, Fi, Fo):
+    return bool(_lib.load().gnnml3_fused_sddmm_supported(int(K), int(Fi), int(Fo)))
+
+
+def fused_sddmm(rowptr, col, x, gc, W, E):
+    """dea[p, k] = <x[col[p]], gc[t] W[k]^T> for every CSR slot p of row t (gnnml3_fused_sddmm) -> [E, K].
+    x [N, Fi] and gc [N, Fo] must satisfy ``aligned_rows``; W [K, Fi, Fo]."""
+    lib = _lib.load()
+    W = _f32c(W, "W")
+    K, Fi, Fo = W.shape
+    N = rowptr.numel() - 1
+    dea = torch.empty(E, K, dtype=torch.float32, device=x.device)
+    ws = _ws(x.device, lib.gnnml3_fused_sddmm_workspace_bytes(K), tag="fused_sddmm")
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gnnml3_fused_sddmm(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(x), _ld(x), Fi, _lib.ptr(gc), _ld(gc), Fo,
+                                          _lib.ptr(W), K, N, _lib.ptr(dea), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "gnnml3_fused_sddmm")
+    return dea
+
+
 def segment_pool_fwd(x, graph_ptr, mean):
     lib = _lib.load()
     x = _f32c(x, "x")
@@ -414,6 +434,6 @@ def _instrument(name, fn):
 
 
 for _n in ("csr_build", "gather_rows", "scatter_rows", "spmm_k", "sddmm_k", "gemm_nn_tc", "gemm_nn", "gemm_tn", "colsum", "edge_mlp_fwd",
-           "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "ml3_act_bwd_y", "fused_agg_proj", "segment_pool_fwd",
+           "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "ml3_act_bwd_y", "fused_agg_proj", "fused_sddmm", "segment_pool_fwd",
            "segment_pool_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

@@ -159,6 +159,19 @@ GNNML3_API int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Fused edge-feature gradient (fused_sddmm.cu):  dea[p, k] = < X[col[p], :], GC[t, :] W[k]^T >  for every CSR slot p of
+ * every row t -- the gradient of SpectConv w.r.t. edge_attr (autograd through libs/spect_conv.py:76-80) without
+ * materialising dH = GC [W_0^T .. W_{K-1}^T] in HBM: per tile of 64 rows the dH tile is produced by tcgen05 MMAs
+ * (3xTF32) into tensor memory, transposed into shared memory and consumed by the SDDMM warps.  W [K, Fi, Fo] contiguous;
+ * X / GC rows 16-byte aligned; dea [E, K] in CSR slot order.  Supported: even K <= 8, Fi <= 32, Fo <= 32.
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_fused_sddmm_supported(int K, int Fi, int Fo);
+GNNML3_API size_t gnnml3_fused_sddmm_workspace_bytes(int K);
+GNNML3_API int gnnml3_fused_sddmm(const int32_t* rowptr, const int32_t* col, const float* X, int64_t ldx, int Fi, const float* GC,
+                       int64_t ldg, int Fo, const float* W, int K, int64_t N, float* dea, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Readout: PyG global_add_pool (mean = 0) / global_mean_pool (mean = 1) over contiguous node ranges
  * graph_ptr [B+1] (graph b owns nodes graph_ptr[b] .. graph_ptr[b+1]-1, as produced by batching).
  * --------------------------------------------------------------------------------------------------- */

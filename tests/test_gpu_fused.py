@@ -130,6 +130,26 @@ def test_fused_large_batch_matches_two_kernel_path():
     assert_close(out, ref, rtol=2e-6, name="fused vs two-kernel")
 
 
+@pytest.mark.parametrize("N,deg,K,Fi,Fo", [(3000, 6, 8, 32, 30), (3001, 5, 8, 25, 30), (1000, 7, 6, 2, 32), (60, 3, 2, 8, 8),
+                                           (100000, 6, 8, 32, 30), (2000, 4, 4, 17, 9)])
+def test_fused_sddmm(N, deg, K, Fi, Fo):
+    """d ea[p, k] = <x[col[p]], gc[t] W_k^T> against float64."""
+    from gnn_matlang_b200 import ops
+    ei, g = _graph(N, deg, 3 * N + K, blk=25)
+    d = dev()
+    plan = ops.csr_build(ei.to(d), N)
+    x = torch.randn(N, Fi, generator=g)
+    gc = torch.randn(N, Fo, generator=g)
+    W = torch.randn(K, Fi, Fo, generator=g) / np.sqrt(Fo)
+    dea = ops.fused_sddmm(plan["rowptr"], plan["col"], ops.aligned_rows(x.to(d)), ops.aligned_rows(gc.to(d)), W.to(d), ei.size(1))
+    rowptr = plan["rowptr"].cpu().long()
+    col = plan["col"].cpu().long()
+    dst = torch.repeat_interleave(torch.arange(N), rowptr[1:] - rowptr[:-1])
+    dH = torch.einsum("no,kio->nki", gc.double(), W.double())              # [N, K, Fi]
+    ref = torch.einsum("ei,eki->ek", x.double()[col], dH[dst])
+    assert_close(dea, ref, name="fused sddmm")
+
+
 def test_act_bwd_y_layout_and_sums():
     from gnn_matlang_b200 import ops
     g = torch.Generator().manual_seed(5)
