@@ -190,7 +190,7 @@ def main():
     # ---- timed region: inputs resident in HBM; successive steps use different batches (ring > L2)
     sampler = ClockSampler(local)
     sampler.start()
-    ops.profile_start(names=["spmm_k"])
+    ops.profile_start(names=["fused_agg_proj"])
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -210,23 +210,33 @@ def main():
     ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel family (K-channel SpMM), from the per-launch events of the timed region
+    # ---- roofline of the dominant kernel (the fused aggregate+project layer kernel: forward launches and the transposed
+    #      dx launches of the backward), from the per-launch CUDA events of the timed region.  achieved = algorithmic bytes
+    #      (every operand and result once; the [N, K*F] aggregate is never credited) / launch time.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    recs = [r for r in recs if r[0] == "fused_agg_proj"]
     sp_ms = sum(r[1] for r in recs)
-    sp_bytes = sum(spmm_bytes(r[2]) for r in recs)
+    sp_bytes = sum(r[2][1] for r in recs)
     roofline = None
     if recs and sp_ms > 0:
         ach = sp_bytes / (sp_ms * 1e-3) / 1e9
-        roofline = {"kernel": "k_spmm (gnnml3_spmm_k, fwd + transposed bwd launches)", "bound": "hbm", "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        try:      # dram bytes per launch from the committed ncu --set full capture of the same kernel (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_fused_kernel_ncu_summary.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"kernel": "k_fused_agg_proj (gnnml3_fused_agg_proj: SpectConv aggregate + projection + gates, fwd and dx launches)",
+                    "bound": "hbm", "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650",
                     "launches": len(recs), "avg_launch_ms": sp_ms / len(recs), "share_of_step": sp_ms / ms,
-                    "algorithmic_bytes_per_launch": sp_bytes / len(recs)}
+                    "algorithmic_bytes_per_launch": sp_bytes / len(recs),
+                    "note": "latency/issue-bound gather + fixed-cost tcgen05.mma issue, see DESIGN.md section 4"}
 
     # ---- kernel breakdown pass (separate, untimed): share of every library call
     breakdown = None

@@ -216,53 +216,69 @@ k_fused_sddmm(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(hempty + hb);          // dH slice is in registers: the buffer may be refilled
             const bool v0 = 8 * g < P.Fi, v1 = 8 * g + 4 < P.Fi;
-            for (int i = 0; i < maxcnt; ++i) {
-                const bool act = i < cnt;
-                float part[KP];
+            // two edges of the row in flight per iteration (index -> gather chain of the second overlaps the first)
+            for (int i = 0; i < maxcnt; i += 2) {
+                float part[2][KP];
+                bool act[2];
 #pragma unroll
-                for (int k = 0; k < KP; ++k) part[k] = 0.f;
-                const int p = rs + i;
-                if (act) {
-                    const int s = __ldg(P.col + p);
-                    const float* xr = P.X + (int64_t)s * P.ldx + 8 * g;
-                    const float4 xa = v0 ? ldg4(xr) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 xb = v1 ? ldg4(xr + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 2; ++u) {
+                    act[u] = i + u < cnt;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        float t = gv[k][0] * xa.x;
-                        t = fmaf(gv[k][1], xa.y, t);
-                        t = fmaf(gv[k][2], xa.z, t);
-                        t = fmaf(gv[k][3], xa.w, t);
-                        t = fmaf(gv[k][4], xb.x, t);
-                        t = fmaf(gv[k][5], xb.y, t);
-                        t = fmaf(gv[k][6], xb.z, t);
-                        t = fmaf(gv[k][7], xb.w, t);
-                        part[k] = t;
+                    for (int k = 0; k < KP; ++k) part[u][k] = 0.f;
+                }
+                float4 xa[2], xb[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    xa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    xb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (act[u]) {
+                        const int s = __ldg(P.col + rs + i + u);
+                        const float* xr = P.X + (int64_t)s * P.ldx + 8 * g;
+                        if (v0) xa[u] = ldg4(xr);
+                        if (v1) xb[u] = ldg4(xr + 4);
                     }
                 }
-                // reduce-scatter over the 4 lanes of the row: 8 -> 4 -> 2 values per lane
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const bool upper = (g & 2) != 0;
-                    const float keep = upper ? part[q4 + 4] : part[q4];
-                    const float send = upper ? part[q4] : part[q4 + 4];
-                    part[q4] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        float t = gv[k][0] * xa[u].x;
+                        t = fmaf(gv[k][1], xa[u].y, t);
+                        t = fmaf(gv[k][2], xa[u].z, t);
+                        t = fmaf(gv[k][3], xa[u].w, t);
+                        t = fmaf(gv[k][4], xb[u].x, t);
+                        t = fmaf(gv[k][5], xb[u].y, t);
+                        t = fmaf(gv[k][6], xb[u].z, t);
+                        t = fmaf(gv[k][7], xb[u].w, t);
+                        part[u][k] = t;
+                    }
                 }
 #pragma unroll
-                for (int q2 = 0; q2 < 2; ++q2) {
-                    const bool upper = (g & 1) != 0;
-                    const float keep = upper ? part[q2 + 2] : part[q2];
-                    const float send = upper ? part[q2] : part[q2 + 2];
-                    part[q2] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                }
-                // lane g now owns channels kbase, kbase + 1 with kbase = 4 * (g >> 1) + 2 * (g & 1)
-                if (act) {
-                    const int kbase = 4 * (g >> 1) + 2 * (g & 1);
-                    float* o = P.dea + (int64_t)p * K + kbase;
-                    if (kbase + 1 < K) {
-                        *reinterpret_cast<float2*>(o) = make_float2(part[0], part[1]);
-                    } else if (kbase < K) {
-                        o[0] = part[0];
+                for (int u = 0; u < 2; ++u) {
+                    // reduce-scatter over the 4 lanes of the row: 8 -> 4 -> 2 values per lane
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const bool upper = (g & 2) != 0;
+                        const float keep = upper ? part[u][q4 + 4] : part[u][q4];
+                        const float send = upper ? part[u][q4] : part[u][q4 + 4];
+                        part[u][q4] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) {
+                        const bool upper = (g & 1) != 0;
+                        const float keep = upper ? part[u][q2 + 2] : part[u][q2];
+                        const float send = upper ? part[u][q2] : part[u][q2 + 2];
+                        part[u][q2] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                    }
+                    // lane g now owns channels kbase, kbase + 1 with kbase = 4 * (g >> 1) + 2 * (g & 1)
+                    if (act[u]) {
+                        const int kbase = 4 * (g >> 1) + 2 * (g & 1);
+                        float* o = P.dea + (int64_t)(rs + i + u) * K + kbase;
+                        if (kbase + 1 < K) {
+                            *reinterpret_cast<float2*>(o) = make_float2(part[u][0], part[u][1]);
+                        } else if (kbase < K) {
+                            o[0] = part[u][0];
+                        }
                     }
                 }
             }

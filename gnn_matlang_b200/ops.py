@@ -327,6 +327,10 @@ def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mod
         bias = _f32c(bias, "bias")
     if bias_s is not None:
         bias_s = _f32c(bias_s, "bias_s")
+    # algorithmic HBM bytes of this launch (every operand once, the [N, K*F] aggregate never counted)
+    E = ea.size(0)
+    _prof["last_bytes"] = 4.0 * (N * F + (N * Fs if (self_mode and S.data_ptr() != x.data_ptr()) else 0) + E * K + E * (2 if eperm is not None else 1)
+                                 + (N + 1) + K * F * Nc + Fs * Ns + Nc + N * W + (N * 2 * G if self_mode == 1 else 0))
     ws = _ws(dev, lib.gnnml3_fused_workspace_bytes(K, F, Nc, self_mode), tag="fused")
     with torch.cuda.device(dev):
         _lib.check(lib.gnnml3_fused_agg_proj(
@@ -401,7 +405,7 @@ def segment_pool_bwd(gout, graph_ptr, mean, N):
 # --------------------------------------------------------------------------------------------------
 # optional per-call device timing (CUDA events on the launching stream) used by bench.py
 # --------------------------------------------------------------------------------------------------
-_prof = {"enabled": False, "names": None, "records": []}
+_prof = {"enabled": False, "names": None, "records": [], "last_bytes": None}
 
 
 def profile_start(names=None):
@@ -426,6 +430,8 @@ def _instrument(name, fn):
         out = fn(*a, **k)
         e.record()
         shapes = tuple(tuple(t.shape) for t in a if isinstance(t, torch.Tensor))
+        if name == "fused_agg_proj":
+            shapes = ("algorithmic_bytes", _prof["last_bytes"])
         _prof["records"].append((name, s, e, shapes))
         return out
     wrapped.__name__ = fn.__name__
