@@ -24,6 +24,14 @@
 // accumulates into the same output columns.  SpectConv(selfconn=True) uses that mode in the forward, too.
 #include "tc_common.cuh"
 
+// cycle counters of the warp roles (gnnml3_fused_debug_counters): compiled in only with -DFL_PROFILE, they cost issue
+// slots and registers in the single-thread control loops that pace the whole kernel
+#ifdef FL_PROFILE
+#define FL_CNT(...) __VA_ARGS__
+#else
+#define FL_CNT(...)
+#endif
+
 namespace gnnml3 {
 
 constexpr int FL_MAX_STAGES = 4;
@@ -48,6 +56,7 @@ struct FLParams {
     int nfh;                // 32-wide feature blocks per support = ceil(F / 32)
     int nkb_main;           // nfh * K
     int pf_rows;            // rows of X prefetched into L1 on either side of a tile (0: off)
+    int slot_cap;           // edges per aggregator-warp prefetch slot (0: the aggregators gather straight from global memory)
     int nstages;            // depth of the H-plane ring (2..4, whatever shared memory is left beside resident weights)
     const float* bias;      // [Nc] or NULL
     const float* bias_s;    // [2G] or NULL (mode 1)
@@ -81,6 +90,26 @@ __device__ __forceinline__ void fl_load_ea(const float* __restrict__ p, float (&
     }
 }
 
+// mbarrier wait with back-off for the control warps (TMA / MMA / epilogue): they spend most of their time waiting and the
+// kernel is instruction-issue bound, so their polling must not take issue slots from the aggregators
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(32);
+    }
+}
+
 __device__ __forceinline__ float fl_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // raw plane + residual plane (LO_OFF bytes behind it) of one 16-byte chunk
@@ -94,6 +123,24 @@ __device__ __forceinline__ void fl_store_chunk(uint8_t* a_raw, uint32_t off, con
 // gate weights form a second M = 64 operand whose accumulator interleaves with the main one in tensor memory at a lane
 // offset of 16) or 64 (Nc <= 64: M = 128, no gates).  RES: all weight planes stay resident in shared memory (loaded once);
 // otherwise the plane of every k-block is streamed from L2 into the stage.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16s(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int KT, int BNH, int NAGG, bool RES>
 __global__ void __launch_bounds__(32 * (FL_CTRL_WARPS + NAGG), 1)
 k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ FLParams P) {
@@ -118,7 +165,8 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     uint64_t* tempty = bars + 2 * FL_MAX_STAGES + 2;   // [2]       accumulator drained                      -> MMA
     uint64_t* wfull = bars + 2 * FL_MAX_STAGES + 4;    // [1]       resident weights landed                  -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FL_MAX_STAGES + 5);
-    int* agg_seq = reinterpret_cast<int*>(tmem_slot + 1);      // tiles started by the aggregators (paces the prefetch warp)
+    int* agg_seq = reinterpret_cast<int*>(tmem_slot + 1);
+    uint8_t* slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars) + 256 + 127) & ~(uintptr_t)127);   // 128-byte aligned    // [NAGG][slot_cap x (128 B source row | Kstride floats)] if slot_cap > 0      // tiles started by the aggregators (paces the prefetch warp)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -154,7 +202,7 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
                     for (int kb = 0; kb < nkb_total; ++kb, ++it) {
                         const uint32_t s = it % nstages;
-                        mbar_wait(empty + s, ((it / nstages) & 1) ^ 1);
+                        mbar_wait_idle(empty + s, ((it / nstages) & 1) ^ 1);
                         mbar_arrive_expect_tx(full + s, WPLANE);
                         tma_load_2d(stages + (size_t)s * STAGE_BYTES + HP_BYTES, &mapW, full + s, 0, kb * MROWS);
                     }
@@ -201,43 +249,49 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         // =================================================================== MMA issuer (one lane)
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32_mn(MROWS, NMMA);
-            if constexpr (RES) mbar_wait(wfull, 0);
-            uint32_t it = 0, tt = 0;
-            long long c_full = 0, c_tempty = 0;
-            const long long c_begin = clock64();
+            if constexpr (RES) mbar_wait_idle(wfull, 0);
+            uint32_t tt = 0, s = 0, sph = 0;                       // stage index / phase kept incrementally (no divisions)
+            const uint32_t stage0 = smem_u32(stages), wres0 = smem_u32(wres);
+            FL_CNT(long long c_full = 0, c_tempty = 0, c_issue = 0; const long long c_begin = clock64();)
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
                 const uint32_t buf = tt & 1;
-                long long c0 = clock64();
-                mbar_wait(tempty + buf, ((tt >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
-                c_tempty += clock64() - c0;
+                FL_CNT(long long c0 = clock64();)
+                mbar_wait_idle(tempty + buf, ((tt >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                FL_CNT(c_tempty += clock64() - c0;)
                 tc_fence_after();
                 const uint32_t d_main = tmem_base + buf * 256;
                 const uint32_t d_gate = d_main + (16u << 16);          // second M = 64 accumulator, interleaved at lane 16
-                for (int kb = 0; kb < nkb_total; ++kb, ++it) {
-                    const uint32_t s = it % nstages;
-                    c0 = clock64();
-                    mbar_wait(full + s, (it / nstages) & 1);
-                    c_full += clock64() - c0;
+                for (int kb = 0; kb < nkb_total; ++kb) {
+                    FL_CNT(c0 = clock64();)
+                    mbar_wait(full + s, sph);
+                    FL_CNT(c_full += clock64() - c0;)
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(stages + (size_t)s * STAGE_BYTES);
+                    const uint32_t sa = stage0 + s * (uint32_t)STAGE_BYTES;
                     const uint64_t dh = make_kmajor_sw128_desc(sa);                 // N side: [H raw ; H lo]  (2 * ROWS rows)
-                    const uint64_t dw = make_kmajor_sw128_desc(RES ? smem_u32(wres + (size_t)kb * WPLANE) : sa + HP_BYTES);
+                    const uint64_t dw = make_kmajor_sw128_desc(RES ? wres0 + (uint32_t)kb * WPLANE : sa + HP_BYTES);
                     const bool gate = P.self_mode == 1 && kb == P.nkb_main;
                     const uint32_t d = gate ? d_gate : d_main;
+                    FL_CNT(const long long ci0 = clock64();)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 8 TF32 = 32 bytes along K inside the swizzled row
                         umma_tf32(d, dw + adv, dh + adv, idesc, ((gate || kb == 0) && k == 0) ? 0u : 1u);
                     }
                     umma_commit(empty + s);                                    // stage reusable once these MMAs retire
+                    FL_CNT(c_issue += clock64() - ci0;)
+                    if (++s == (uint32_t)nstages) {
+                        s = 0;
+                        sph ^= 1;
+                    }
                 }
                 umma_commit(tfull + buf);                                      // tile complete -> epilogue
             }
-            if (P.dbg) {
+            FL_CNT(if (P.dbg) {
                 atomicAdd(P.dbg + 3, (unsigned long long)c_full);
                 atomicAdd(P.dbg + 4, (unsigned long long)c_tempty);
                 atomicAdd(P.dbg + 5, (unsigned long long)(clock64() - c_begin));
-            }
+                atomicAdd(P.dbg + 10, (unsigned long long)c_issue);
+            })
         }
     } else if (warp < 4) {
         // =================================================================== epilogue (128 threads)
@@ -258,13 +312,12 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         const int fr = et >> 2, fg = et & 3;                           // finishing role: row of the chunk, column group
         const bool vec_out = (P.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
         uint32_t tt = 0;
-        long long c_tfull = 0;
-        const long long c_begin = clock64();
+        FL_CNT(long long c_tfull = 0; const long long c_begin = clock64();)
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
             const uint32_t buf = tt & 1;
-            const long long cw = clock64();
-            mbar_wait(tfull + buf, (tt >> 1) & 1);
-            c_tfull += clock64() - cw;
+            FL_CNT(const long long cw = clock64();)
+            mbar_wait_idle(tfull + buf, (tt >> 1) & 1);
+            FL_CNT(c_tfull += clock64() - cw;)
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
             const int64_t row0 = (int64_t)tile * ROWS;
@@ -335,10 +388,10 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + buf);
         }
-        if (P.dbg && lane == 0) {
+        FL_CNT(if (P.dbg && lane == 0) {
             atomicAdd(P.dbg + 6, (unsigned long long)c_tfull);
             atomicAdd(P.dbg + 7, (unsigned long long)(clock64() - c_begin));
-        }
+        })
     } else if (warp >= FL_CTRL_WARPS) {
         // =================================================================== aggregators
         const int aw = warp - FL_CTRL_WARPS;
@@ -356,14 +409,223 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         const int64_t ldx = P.ldx;
         const int Kstride = P.Kstride;
         uint32_t it = 0;
-        long long c_gather = 0, c_wait = 0;
-        const long long c_begin = clock64();
+        FL_CNT(long long c_gather = 0, c_wait = 0; const long long c_begin = clock64();)
+        uint32_t st_i = 0, st_ph = 1;                    // H-plane stage index / producer parity, kept incrementally
         int tseq = 0;
+        if (P.slot_cap > 0) {
+            // ------------------------------------------------------------------------------------------------------------
+            // Self-prefetching mode (one 32-wide feature block per support).  The rows of a warp are consecutive, so their
+            // CSR slots [eb, ee) are contiguous: while the tile's finished k-blocks are handed to the tensor core, the warp
+            // already streams the NEXT tile's source rows and edge weights into its private shared-memory slot with 16-byte
+            // cp.async copies (no registers held, every edge of the 8 rows in flight at once); the CSR slots of the tile after
+            // that and the row bounds of the one after are fetched in the same step, so every dependent global latency
+            // (rowptr -> col -> source row) is hidden behind a whole tile period.  The FMAs then read shared memory only.
+            // ------------------------------------------------------------------------------------------------------------
+            const int CAP = P.slot_cap;
+            if (aw == 0 && lane == 0) *reinterpret_cast<volatile int*>(agg_seq) = 1 << 30;      // never hold the L1 prefetch warp back
+            const int KC = Kstride >> 2;                                   // 16-byte chunks per edge-weight row
+            uint8_t* xs = slots + (size_t)aw * CAP * (128 + 4 * Kstride);  // [CAP][128 B], chunk c of edge pos at (c ^ (pos & 7))
+            float* es = reinterpret_cast<float*>(xs + (size_t)CAP * 128);  // [CAP][Kstride]
+            const uint32_t xs32 = smem_u32(xs), es32 = smem_u32(es);
+            const int kc_shift = KC == 1 ? 0 : (KC == 2 ? 1 : (KC == 4 ? 2 : -1));   // KC = 3 takes the division
+            const int nchunk = (P.F + 3) >> 2;                             // valid 16-byte chunks of a source row
+            auto bounds = [&](int tile) -> int {                           // lane l <- rowptr[first row of the warp + l], l <= 8
+                int v = 0;
+                if (tile < P.n_tiles) {
+                    const int64_t r = (int64_t)tile * ROWS + aw * 8 + (lane < 8 ? lane : 8);
+                    v = __ldg(rowptr + (r < P.N ? r : P.N));
+                }
+                return v;
+            };
+            auto loadcols = [&](int ebv, int (&cv)[2], int (&pv)[2]) {
+                const int eb = __shfl_sync(0xffffffffu, ebv, 0), n = __shfl_sync(0xffffffffu, ebv, 8) - eb;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int e = eb + 32 * b + lane;
+                    const bool ok = 32 * b + lane < n && n <= CAP;
+                    cv[b] = ok ? __ldg(col + e) : 0;
+                    pv[b] = ok ? (eperm ? __ldg(eperm + e) : e) : 0;
+                }
+            };
+            auto issue = [&](int ebv, const int (&cv)[2], const int (&pv)[2]) {
+                const int eb = __shfl_sync(0xffffffffu, ebv, 0), n = __shfl_sync(0xffffffffu, ebv, 8) - eb;
+                if (n <= CAP) {
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        if (32 * b < n) {
+                            const int c = lane & 7;
+                            const float* xcol = X + 4 * c;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {                  // 4 edges x 8 chunks per instruction: whole 128-byte lines
+                                const int j = 4 * i + (lane >> 3), pos = 32 * b + j;
+                                const int sidx = __shfl_sync(0xffffffffu, cv[b], j);
+                                if (pos < n && c < nchunk)
+                                    cp_async_16s(xs32 + (uint32_t)pos * 128u + (uint32_t)((c ^ (pos & 7)) << 4), xcol + (int64_t)sidx * ldx);
+                            }
+                            for (int i0 = 0; i0 < KC; ++i0) {
+                                const int idx = i0 * 32 + lane;
+                                const int j = kc_shift >= 0 ? (idx >> kc_shift) : idx / KC;
+                                const int h = idx - j * KC, pos = 32 * b + j;
+                                const int pe = __shfl_sync(0xffffffffu, pv[b], j);
+                                if (pos < n)
+                                    cp_async_16s(es32 + (uint32_t)(pos * Kstride + 4 * h) * 4u, ea + (int64_t)pe * Kstride + 4 * h);
+                            }
+                        }
+                    }
+                }
+            };
+            const int t0 = blockIdx.x, gs = gridDim.x;
+            int ebvA = bounds(t0), ebvB = bounds(t0 + gs), ebvC = bounds(t0 + 2 * gs);
+            int cvB[2], pvB[2];
+            {
+                int cvA[2], pvA[2];
+                loadcols(ebvA, cvA, pvA);
+                issue(ebvA, cvA, pvA);
+            }
+            loadcols(ebvB, cvB, pvB);
+            for (int tile = t0; tile < P.n_tiles; tile += gs) {
+                FL_CNT(long long cg0 = clock64();)
+                const int eb = __shfl_sync(0xffffffffu, ebvA, 0), ntile = __shfl_sync(0xffffffffu, ebvA, 8) - eb;
+                const int rs = __shfl_sync(0xffffffffu, ebvA, rq), re = __shfl_sync(0xffffffffu, ebvA, rq + 1);
+                const bool staged = ntile <= CAP;
+                cp_async_wait_all();
+                __syncwarp();
+                const int f0 = g * 4, f1 = f0 + 16;
+                const bool v0 = f0 < P.F, v1 = f1 < P.F;
+                for (int k0 = 0; k0 < P.K; k0 += KT) {
+                    float acc[KT][8];
+#pragma unroll
+                    for (int k = 0; k < KT; ++k)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+                    if (staged) {
+                        // edges of a row in their original order (the reference's CPU order); operands from the warp's slot
+                        uint32_t xa_addr = xs32 + (uint32_t)(rs - eb) * 128u;
+                        uint32_t w_addr = es32 + (uint32_t)((rs - eb) * Kstride + k0) * 4u;
+                        int sw = ((rs - eb) & 7) << 4;
+                        const uint32_t wstep = (uint32_t)Kstride * 4u;
+                        for (int p = rs; p < re; ++p) {
+                            float w[KT];
+                            if constexpr (KT % 4 == 0) {
+#pragma unroll
+                                for (int k = 0; k < KT; k += 4) {
+                                    const float4 t = lds128(w_addr + 4 * k);
+                                    w[k] = t.x; w[k + 1] = t.y; w[k + 2] = t.z; w[k + 3] = t.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < KT; ++k) w[k] = lds32(w_addr + 4 * k);
+                            }
+                            const uint32_t a0 = xa_addr + (uint32_t)((g << 4) ^ sw);
+                            float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+                            if (v0) xa = lds128(a0);
+                            if (v1) xb = lds128(a0 ^ 64u);
+                            xa_addr += 128u;
+                            w_addr += wstep;
+                            sw = (sw + 16) & 112;
+#pragma unroll
+                            for (int k = 0; k < KT; ++k) {
+                                acc[k][0] = fmaf(w[k], xa.x, acc[k][0]);
+                                acc[k][1] = fmaf(w[k], xa.y, acc[k][1]);
+                                acc[k][2] = fmaf(w[k], xa.z, acc[k][2]);
+                                acc[k][3] = fmaf(w[k], xa.w, acc[k][3]);
+                                acc[k][4] = fmaf(w[k], xb.x, acc[k][4]);
+                                acc[k][5] = fmaf(w[k], xb.y, acc[k][5]);
+                                acc[k][6] = fmaf(w[k], xb.z, acc[k][6]);
+                                acc[k][7] = fmaf(w[k], xb.w, acc[k][7]);
+                            }
+                        }
+                    } else {
+                        for (int p = rs; p < re; ++p) {        // more edges than the slot holds: straight from global memory
+                            float w[KT];
+                            float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+                            const int sidx = __ldg(col + p);
+                            const int eidx = eperm ? __ldg(eperm + p) : p;
+#pragma unroll
+                            for (int k = 0; k < KT; ++k) w[k] = __ldg(ea + (int64_t)eidx * Kstride + k0 + k);
+                            const float* xr = X + (int64_t)sidx * ldx;
+                            if (v0) xa = ldg4(xr + f0);
+                            if (v1) xb = ldg4(xr + f1);
+#pragma unroll
+                            for (int k = 0; k < KT; ++k) {
+                                acc[k][0] = fmaf(w[k], xa.x, acc[k][0]);
+                                acc[k][1] = fmaf(w[k], xa.y, acc[k][1]);
+                                acc[k][2] = fmaf(w[k], xa.z, acc[k][2]);
+                                acc[k][3] = fmaf(w[k], xa.w, acc[k][3]);
+                                acc[k][4] = fmaf(w[k], xb.x, acc[k][4]);
+                                acc[k][5] = fmaf(w[k], xb.y, acc[k][5]);
+                                acc[k][6] = fmaf(w[k], xb.z, acc[k][6]);
+                                acc[k][7] = fmaf(w[k], xb.w, acc[k][7]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    FL_CNT(c_gather += clock64() - cg0;)
+                    if (k0 + KT >= P.K) {
+                        // the slot is free: stream the next tile in, fetch the CSR slots / bounds of the two after it
+                        issue(ebvB, cvB, pvB);
+                        ebvA = ebvB;
+                        ebvB = ebvC;
+                        loadcols(ebvB, cvB, pvB);
+                        ebvC = bounds(tile + 3 * gs);
+                    }
+#pragma unroll
+                    for (int k = 0; k < KT; ++k, ++it) {
+                        const uint32_t s = st_i;
+                        FL_CNT(const long long cw = clock64();)
+                        mbar_wait(empty + s, st_ph);
+                        FL_CNT(c_wait += clock64() - cw;)
+                        uint8_t* a_raw = stages + (size_t)s * STAGE_BYTES;
+                        if (++st_i == (uint32_t)nstages) {
+                            st_i = 0;
+                            st_ph ^= 1;
+                        }
+                        fl_store_chunk<ROWS * 128>(a_raw, off0, &acc[k][0]);
+                        fl_store_chunk<ROWS * 128>(a_raw, off1, &acc[k][4]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full + s);
+                    }
+                    FL_CNT(cg0 = clock64();)
+                }
+                if (P.self_mode != 0) {
+                    const int64_t row = (int64_t)tile * ROWS + rloc;
+                    float sv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sv[i] = 0.f;
+                    if (row < P.N) {
+                        const float* sr = P.S + row * P.lds;
+                        if (g * 4 < P.Fs) {
+                            const float4 t = ldg4(sr + g * 4);
+                            sv[0] = t.x; sv[1] = t.y; sv[2] = t.z; sv[3] = t.w;
+                        }
+                        if (16 + g * 4 < P.Fs) {
+                            const float4 t = ldg4(sr + 16 + g * 4);
+                            sv[4] = t.x; sv[5] = t.y; sv[6] = t.z; sv[7] = t.w;
+                        }
+                    }
+                    const uint32_t s = st_i;
+                    mbar_wait(empty + s, st_ph);
+                    uint8_t* a_raw = stages + (size_t)s * STAGE_BYTES;
+                    if (++st_i == (uint32_t)nstages) {
+                        st_i = 0;
+                        st_ph ^= 1;
+                    }
+                    fl_store_chunk<ROWS * 128>(a_raw, off0, &sv[0]);
+                    fl_store_chunk<ROWS * 128>(a_raw, off1, &sv[4]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full + s);
+                    ++it;
+                }
+            }
+            cp_async_wait_all();
+        } else
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             if (aw == 0 && lane == 0) *reinterpret_cast<volatile int*>(agg_seq) = ++tseq;
             const int64_t row = (int64_t)tile * ROWS + rloc;
             int rs = 0, re = 0;
-            long long cg0 = clock64();
+            FL_CNT(long long cg0 = clock64();)
             if (row < P.N) {
                 rs = __ldg(rowptr + row);
                 re = __ldg(rowptr + row + 1);
@@ -430,21 +692,25 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                     }
                     // hand the KT finished k-blocks to the tensor core
                     __syncwarp();
-                    c_gather += clock64() - cg0;
+                    FL_CNT(c_gather += clock64() - cg0;)
 #pragma unroll
                     for (int k = 0; k < KT; ++k, ++it) {
-                        const uint32_t s = it % nstages;
-                        const long long cw = clock64();
-                        mbar_wait(empty + s, ((it / nstages) & 1) ^ 1);
-                        c_wait += clock64() - cw;
+                        const uint32_t s = st_i;
+                        FL_CNT(const long long cw = clock64();)
+                        mbar_wait(empty + s, st_ph);
+                        FL_CNT(c_wait += clock64() - cw;)
                         uint8_t* a_raw = stages + (size_t)s * STAGE_BYTES;
+                        if (++st_i == (uint32_t)nstages) {
+                            st_i = 0;
+                            st_ph ^= 1;
+                        }
                         fl_store_chunk<ROWS * 128>(a_raw, off0, &acc[k][0]);
                         fl_store_chunk<ROWS * 128>(a_raw, off1, &acc[k][4]);
                         fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full + s);
                     }
-                    cg0 = clock64();
+                    FL_CNT(cg0 = clock64();)
                 }
             }
             if (P.self_mode != 0) {
@@ -462,9 +728,13 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         sv[4] = t.x; sv[5] = t.y; sv[6] = t.z; sv[7] = t.w;
                     }
                 }
-                const uint32_t s = it % nstages;
-                mbar_wait(empty + s, ((it / nstages) & 1) ^ 1);
+                const uint32_t s = st_i;
+                mbar_wait(empty + s, st_ph);
                 uint8_t* a_raw = stages + (size_t)s * STAGE_BYTES;
+                if (++st_i == (uint32_t)nstages) {
+                    st_i = 0;
+                    st_ph ^= 1;
+                }
                 fl_store_chunk<ROWS * 128>(a_raw, off0, &sv[0]);
                 fl_store_chunk<ROWS * 128>(a_raw, off1, &sv[4]);
                 fence_proxy_async_smem();
@@ -473,11 +743,11 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 ++it;
             }
         }
-        if (P.dbg && lane == 0) {
+        FL_CNT(if (P.dbg && lane == 0) {
             atomicAdd(P.dbg + 0, (unsigned long long)c_gather);
             atomicAdd(P.dbg + 1, (unsigned long long)c_wait);
             atomicAdd(P.dbg + 2, (unsigned long long)(clock64() - c_begin));
-        }
+        })
     }
     tc_fence_before();
     __syncthreads();
@@ -537,12 +807,12 @@ static const bool g_fl_debug = [] {
 
 extern "C" int gnnml3_fused_debug_counters(unsigned long long* out8_host, int reset) {
     if (!g_fl_dbg) {
-        for (int i = 0; i < 8; ++i) out8_host[i] = 0;
+        for (int i = 0; i < 16; ++i) out8_host[i] = 0;
         return GNNML3_OK;
     }
     GNNML3_CUDA(cudaDeviceSynchronize());
-    GNNML3_CUDA(cudaMemcpy(out8_host, g_fl_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    if (reset) GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 8 * sizeof(unsigned long long)));
+    GNNML3_CUDA(cudaMemcpy(out8_host, g_fl_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 16 * sizeof(unsigned long long)));
     return GNNML3_OK;
 }
 
@@ -573,7 +843,7 @@ extern "C" size_t gnnml3_fused_workspace_bytes(int K, int F, int Nc, int self_mo
 }
 
 constexpr size_t FL_SMEM_MAX = 227 * 1024;                                              // opt-in limit per CTA on sm_100
-constexpr size_t FL_SMEM_FIXED = 2 * FL_XCH * sizeof(float) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr size_t FL_SMEM_FIXED = 2 * FL_XCH * sizeof(float) + 1024 /*alignment slack*/ + 256 /*barriers*/ + 128 /*slot alignment*/;
 
 template <int KT, int BNH, int NAGG, bool RES>
 static int fl_launch2(const CUtensorMap& mW, FLParams& P, size_t smem, cudaStream_t st) {
@@ -591,6 +861,29 @@ static int fl_launch2(const CUtensorMap& mW, FLParams& P, size_t smem, cudaStrea
 
 // Weight planes stay resident in shared memory when at least 3 H-plane stages fit beside them; otherwise every k-block's
 // plane is streamed from L2 into its stage (large K * F: L2-bandwidth bound).
+// Aggregator mode (gnnml3_fused_set_mode): 0 = gather straight from global memory, weight planes resident (default: the
+// two modes measure the same on B200 -- the kernel is paced by the plane hand-off / MMA chain, see DESIGN.md -- and this is
+// the simpler one); 1 = per-warp cp.async prefetch slots.  GNNML3_FUSED_SLOT=1 selects mode 1 at load time.
+static int g_fl_slot_mode = [] {
+    const char* e = getenv("GNNML3_FUSED_SLOT");
+    return (e && e[0] == '1') ? 1 : 0;
+}();
+#define g_fl_no_slot (g_fl_slot_mode == 0)
+
+extern "C" int gnnml3_fused_set_mode(int slot_mode) {
+    const int old = g_fl_slot_mode;
+    if (slot_mode == 0 || slot_mode == 1) g_fl_slot_mode = slot_mode;
+    return old;
+}
+
+static const size_t g_fl_max_stages = [] {
+    const char* e = getenv("GNNML3_FUSED_MAXSTAGES");       // experiments: cap the depth of the H-plane ring
+    return (size_t)(e ? atoi(e) : FL_MAX_STAGES);
+}();
+
+// Shared-memory plan.  Preferred: per-warp prefetch slots (64 edges each) + as many H-plane stages as fit, weight planes
+// resident if there is still room for 3 stages, otherwise streamed from L2 into the stages.  Without slots (wide feature
+// blocks, odd edge-weight strides): resident weights when 3 stages fit beside them, else streamed.
 template <int KT, int BNH, int NAGG>
 static int fl_launch(const CUtensorMap& mW, FLParams& P, cudaStream_t st) {
     constexpr int ROWS = 8 * NAGG;
@@ -598,23 +891,55 @@ static int fl_launch(const CUtensorMap& mW, FLParams& P, cudaStream_t st) {
     P.n_tiles = cdiv(P.N, ROWS);
     const size_t nkb_total = P.nkb_main + (P.self_mode != 0 ? 1 : 0);
     const size_t resident = nkb_total * WPLANE;
+    const size_t slot_cap = 64;
+    const size_t slots = (P.nfh == 1 && P.Kstride % 4 == 0 && P.Kstride <= 16 && !g_fl_no_slot)
+                             ? (size_t)NAGG * slot_cap * (128 + 4 * (size_t)P.Kstride) : 0;
+    P.slot_cap = 0;
+    if (slots) {
+        if (resident + slots + 3 * HP + FL_SMEM_FIXED <= FL_SMEM_MAX) {
+            size_t ns = (FL_SMEM_MAX - FL_SMEM_FIXED - resident - slots) / HP;
+            if (ns > FL_MAX_STAGES) ns = FL_MAX_STAGES;
+        if (ns > g_fl_max_stages) ns = g_fl_max_stages;
+            P.nstages = (int)ns;
+            P.slot_cap = (int)slot_cap;
+            return fl_launch2<KT, BNH, NAGG, true>(mW, P, resident + ns * HP + FL_SMEM_FIXED + slots, st);
+        }
+        if (slots + 2 * (HP + WPLANE) + FL_SMEM_FIXED <= FL_SMEM_MAX) {
+            size_t ns = (FL_SMEM_MAX - FL_SMEM_FIXED - slots) / (HP + WPLANE);
+            if (ns > FL_MAX_STAGES) ns = FL_MAX_STAGES;
+        if (ns > g_fl_max_stages) ns = g_fl_max_stages;
+            P.nstages = (int)ns;
+            P.slot_cap = (int)slot_cap;
+            return fl_launch2<KT, BNH, NAGG, false>(mW, P, ns * (HP + WPLANE) + FL_SMEM_FIXED + slots, st);
+        }
+    }
     if (resident + 3 * HP + FL_SMEM_FIXED <= FL_SMEM_MAX) {
         size_t ns = (FL_SMEM_MAX - FL_SMEM_FIXED - resident) / HP;
         if (ns > FL_MAX_STAGES) ns = FL_MAX_STAGES;
+        if (ns > g_fl_max_stages) ns = g_fl_max_stages;
         P.nstages = (int)ns;
         return fl_launch2<KT, BNH, NAGG, true>(mW, P, resident + ns * HP + FL_SMEM_FIXED, st);
     }
     size_t ns = (FL_SMEM_MAX - FL_SMEM_FIXED) / (HP + WPLANE);
     if (ns > FL_MAX_STAGES) ns = FL_MAX_STAGES;
+        if (ns > g_fl_max_stages) ns = g_fl_max_stages;
     P.nstages = (int)ns;
     return fl_launch2<KT, BNH, NAGG, false>(mW, P, ns * (HP + WPLANE) + FL_SMEM_FIXED, st);
 }
 
 // aggregator warps per CTA by register need: KT x 8 accumulators per lane.  512 threads leave 128 registers per thread
 // (KT >= 7), 640 threads 96 (KT <= 6); the 16-warp / 4-supports-per-pass variant runs at 80.
+// K supports are processed in register tiles of KT; with the prefetch slots (operands re-read from shared memory at no
+// global cost) K = 8 runs as two passes of 4 so that the tensor core works on the first four k-blocks while the second
+// pass accumulates (GNNML3_FUSED_SPLIT=0 restores the single pass).
+static const bool g_fl_split = [] {
+    const char* e = getenv("GNNML3_FUSED_SPLIT");
+    return !(e && e[0] == '0');
+}();
+
 #define FL_DISPATCH_KT(KTV, BNV)                                                                      \
     switch (KTV) {                                                                                    \
-        case 4: return fl_launch<4, BNV, 14>(mW, P, st);                                              \
+        case 4: return (K == 8) ? fl_launch<4, BNV, 10>(mW, P, st) : fl_launch<4, BNV, 14>(mW, P, st); \
         case 5: return fl_launch<5, BNV, 14>(mW, P, st);                                              \
         case 6: return fl_launch<6, BNV, 14>(mW, P, st);                                              \
         case 7: return fl_launch<7, BNV, 10>(mW, P, st);                                              \
@@ -644,8 +969,9 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
         return set_err(GNNML3_ERR_WORKSPACE, "fused_agg_proj: workspace too small");
     cudaStream_t st = (cudaStream_t)stream_;
     const int BNH = fl_bnh_for(Nc);
-    const int KT = fl_kt_for(K);
+    int KT = fl_kt_for(K);
     const int nfh = cdiv(F, 32);
+    if (K == 8 && g_fl_split && nfh == 1 && Kstride % 4 == 0 && !g_fl_no_slot) KT = 4;
     const int nkb_main = nfh * K;
     const int nkb_total = nkb_main + (self_mode != 0 ? 1 : 0);
     float* planes = (float*)workspace;
@@ -661,12 +987,12 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
     FLParams P;
     P.rowptr = rowptr; P.col = col; P.eperm = eperm; P.ea = ea; P.Kstride = Kstride; P.K = K;
     P.X = X; P.ldx = ldx; P.F = F; P.S = S; P.lds = lds; P.Fs = Fs; P.self_mode = self_mode;
-    P.N = N; P.n_tiles = 0; P.nfh = nfh; P.nkb_main = nkb_main; P.nstages = 0; P.pf_rows = g_fl_pf_rows;
+    P.N = N; P.n_tiles = 0; P.nfh = nfh; P.nkb_main = nkb_main; P.nstages = 0; P.pf_rows = g_fl_pf_rows; P.slot_cap = 0;
     P.bias = bias; P.bias_s = bias_s; P.out = out; P.ldo = ldo; P.Nc = Nc; P.aux = aux; P.ldaux = ldaux; P.G = G;
     P.epi = epilogue;
     if (g_fl_debug && !g_fl_dbg) {
-        GNNML3_CUDA(cudaMalloc(&g_fl_dbg, 8 * sizeof(unsigned long long)));
-        GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 8 * sizeof(unsigned long long)));
+        GNNML3_CUDA(cudaMalloc(&g_fl_dbg, 16 * sizeof(unsigned long long)));
+        GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 16 * sizeof(unsigned long long)));
     }
     P.dbg = g_fl_dbg;
     if (g_fl_nagg16 && K % 4 == 0 && Kstride % 4 == 0) {     // experiment: 16 aggregator warps, 4 supports per pass

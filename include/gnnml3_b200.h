@@ -149,6 +149,9 @@ GNNML3_API int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* au
  * --------------------------------------------------------------------------------------------------- */
 /* debugging aid: cycle counters of the fused kernel's warp roles (all zero unless GNNML3_FUSED_DEBUG=1); synchronises */
 GNNML3_API int gnnml3_fused_debug_counters(unsigned long long* out8_host, int reset);
+/* aggregator mode of gnnml3_fused_agg_proj: 0 (default) gathers from global memory with the weight planes resident in shared
+ * memory, 1 prefetches every warp's next tile into shared-memory slots with cp.async; returns the previous mode */
+GNNML3_API int gnnml3_fused_set_mode(int slot_mode);
 GNNML3_API int gnnml3_fused_supported(int K, int Kstride, int F, int Nc, int Fs, int self_mode, int Ns);
 GNNML3_API size_t gnnml3_fused_workspace_bytes(int K, int F, int Nc, int self_mode);
 GNNML3_API int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea,

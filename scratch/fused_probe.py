@@ -36,12 +36,13 @@ def timeit(fn, name):
     if os.environ.get("GNNML3_FUSED_DEBUG") == "1" and name.startswith("fused"):
         import ctypes
         from gnn_matlang_b200 import _lib
-        buf = (ctypes.c_ulonglong * 8)()
+        buf = (ctypes.c_ulonglong * 16)()
         _lib.load().gnnml3_fused_debug_counters(buf, 1)
         c = [float(v) / (reps + 1) for v in buf]
         nagg = c[2] and round(c[2] / (c[5] or 1))
         print("   per launch (cycles summed over CTAs): agg gather %.3g wait %.3g total %.3g | mma wait_full %.3g wait_tempty %.3g total %.3g | epi wait %.3g total %.3g"
-              % tuple(c))
+              % tuple(c[:8]))
+        print("   mma issue+commit cycles per CTA %.3g (of total %.3g)" % (c[10] / 148, c[5] / 148))
         print("   fractions: agg gather %.2f wait %.2f | mma wait_full %.2f wait_tempty %.2f busy %.2f | epi wait %.2f"
               % (c[0] / c[2], c[1] / c[2], c[3] / c[5], c[4] / c[5], 1 - (c[3] + c[4]) / c[5], c[6] / c[7]))
 

@@ -44,8 +44,18 @@ CASES = [  # N, deg, K, F, Nc, G
 ]
 
 
+@pytest.fixture(params=[0, 1], ids=["gather-global", "prefetch-slots"])
+def fused_mode(request):
+    """Both aggregator modes of the fused kernel (gnnml3_fused_set_mode)."""
+    from gnn_matlang_b200 import _lib
+    lib = _lib.load()
+    old = lib.gnnml3_fused_set_mode(request.param)
+    yield request.param
+    lib.gnnml3_fused_set_mode(old)
+
+
 @pytest.mark.parametrize("N,deg,K,F,Nc,G", CASES)
-def test_fused_forward_ml3(N, deg, K, F, Nc, G):
+def test_fused_forward_ml3(N, deg, K, F, Nc, G, fused_mode):
     from gnn_matlang_b200 import ops
     if deg == 0:
         pytest.skip("E == 0 takes the unfused host path")
@@ -84,7 +94,7 @@ def test_fused_forward_ml3(N, deg, K, F, Nc, G):
 
 @pytest.mark.parametrize("N,deg,K,F,Nc,Fs", [(3000, 6, 8, 30, 32, 4), (2000, 5, 6, 32, 2, 32), (1200, 4, 10, 64, 64, 0),
                                               (1000, 6, 12, 16, 32, 32)])
-def test_fused_transposed_with_self_block(N, deg, K, F, Nc, Fs):
+def test_fused_transposed_with_self_block(N, deg, K, F, Nc, Fs, fused_mode):
     """The dx form: transposed CSR, edge weights through permT, a self block accumulating into the main columns."""
     from gnn_matlang_b200 import ops
     ei, g = _graph(N, deg, 7 * N + K)
@@ -114,7 +124,7 @@ def test_fused_transposed_with_self_block(N, deg, K, F, Nc, Fs):
     assert_close(out, ref, name="dx form")
 
 
-def test_fused_large_batch_matches_two_kernel_path():
+def test_fused_large_batch_matches_two_kernel_path(fused_mode):
     """ZINC bench shape (many tiles per SM): fused result == SpMM + GEMM of the same library."""
     from gnn_matlang_b200 import ops
     N, deg, K, F, Nc = 150000, 6, 8, 32, 30
