@@ -937,9 +937,14 @@ static const bool g_fl_split = [] {
     return !(e && e[0] == '0');
 }();
 
+static const bool g_fl_wide = [] {
+    const char* e = getenv("GNNML3_FUSED_WIDE");      // experiment: K = 8 as two passes of 4 with 14 aggregator warps (112-row tiles)
+    return e && e[0] == '1';
+}();
+
 #define FL_DISPATCH_KT(KTV, BNV)                                                                      \
     switch (KTV) {                                                                                    \
-        case 4: return (K == 8) ? fl_launch<4, BNV, 10>(mW, P, st) : fl_launch<4, BNV, 14>(mW, P, st); \
+        case 4: return (K == 8 && !g_fl_wide) ? fl_launch<4, BNV, 10>(mW, P, st) : fl_launch<4, BNV, 14>(mW, P, st); \
         case 5: return fl_launch<5, BNV, 14>(mW, P, st);                                              \
         case 6: return fl_launch<6, BNV, 14>(mW, P, st);                                              \
         case 7: return fl_launch<7, BNV, 10>(mW, P, st);                                              \
@@ -972,6 +977,7 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
     int KT = fl_kt_for(K);
     const int nfh = cdiv(F, 32);
     if (K == 8 && g_fl_split && nfh == 1 && Kstride % 4 == 0 && !g_fl_no_slot) KT = 4;
+    if (K == 8 && g_fl_wide) KT = 4;
     const int nkb_main = nfh * K;
     const int nkb_total = nkb_main + (self_mode != 0 ? 1 : 0);
     float* planes = (float*)workspace;

@@ -61,29 +61,42 @@ def _aggregate(plan, ea_s, x, width_blocks, transposed=False):
 
 
 class _SpectConvFn(torch.autograd.Function):
-    """out = sum_k P_k(x) W_k (+ x W_K if selfconn) (+ bias)   -- reference libs/spect_conv.py:70-80,93-94."""
+    """out = sum_k P_k(x) W_k (+ x W_K if selfconn) (+ bias)   -- reference libs/spect_conv.py:70-80,93-94.
+
+    Forward and d x run as ONE fused tcgen05 kernel each (aggregate + projection, the [N, K*Fi] aggregate never exists;
+    selfconn rides along as one more k-block); d edge_attr through the fused dH + SDDMM kernel; shapes outside the fused
+    kernels' envelope take the two-kernel path (SpMM + GEMM)."""
 
     @staticmethod
     def forward(ctx, x, ea_s, weight, bias, plan, selfconn, precision):
-        x = x.contiguous()
+        if x.stride(1) != 1:
+            x = x.contiguous()
         ea_s = ea_s.contiguous()
         weight = weight.contiguous()
         N, Fi = x.shape
         Kw, _, Fo = weight.shape
         K = ea_s.size(1)
-        H = _aggregate(plan, ea_s, x, Kw)
-        if selfconn:
-            H[:, K * Fi:] = x
-        out = ops.gemm_nn(H, weight.view(Kw * Fi, Fo), bias, precision=precision)
-        ctx.save_for_backward(x, ea_s, weight)
+        fused = (_use_fused(precision) and N > 0 and plan.E > 0 and (not selfconn or Fi <= 32)
+                 and ops.fused_supported(K, K, Fi, Fo, Fi if selfconn else 0, 2 if selfconn else 0, 0))
         ctx.plan, ctx.selfconn, ctx.precision, ctx.has_bias = plan, selfconn, precision, bias is not None
+        ctx.fused = fused
+        if fused:
+            x = ops.aligned_rows(x)
+            out, _ = ops.fused_agg_proj(plan.rowptr, plan.col, None, ea_s, x, weight[:K].reshape(K * Fi, Fo), bias=bias,
+                                        S=x if selfconn else None, self_mode=2 if selfconn else 0,
+                                        Bself=weight[K] if selfconn else None, epilogue=0)
+        else:
+            H = _aggregate(plan, ea_s, x, Kw)
+            if selfconn:
+                H[:, K * Fi:] = x
+            out = ops.gemm_nn(H, weight.view(Kw * Fi, Fo), bias, precision=precision)
+        ctx.save_for_backward(x, ea_s, weight)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         x, ea_s, weight = ctx.saved_tensors
         plan, prec = ctx.plan, ctx.precision
-        gout = gout.contiguous()
         N, Fi = x.shape
         Kw, _, Fo = weight.shape
         K = ea_s.size(1)
@@ -93,11 +106,20 @@ class _SpectConvFn(torch.autograd.Function):
             return (torch.zeros_like(x) if need_x else None, torch.zeros_like(ea_s) if need_ea else None,
                     torch.zeros_like(weight) if need_w else None,
                     torch.zeros(Fo, device=x.device) if (need_b and ctx.has_bias) else None, None, None, None)
-        if need_x or need_w:
+        gout = ops.aligned_rows(gout) if ctx.fused else gout.contiguous()
+        fused_dx = (ctx.fused and need_x and (not ctx.selfconn or Fo <= 32)
+                    and ops.fused_supported(K, K, Fo, Fi, Fo if ctx.selfconn else 0, 2 if ctx.selfconn else 0, 0))
+        if fused_dx:
+            # dx = sum_k S_k^T gout W_k^T (+ gout W_K^T): the same fused kernel over the transposed CSR
+            dx, _ = ops.fused_agg_proj(plan.rowptrT, plan.colT, plan.permT, ea_s, gout,
+                                       weight[:K].transpose(1, 2).reshape(K * Fo, Fi).contiguous(),
+                                       S=gout if ctx.selfconn else None, self_mode=2 if ctx.selfconn else 0,
+                                       Bself=weight[K].t().contiguous() if ctx.selfconn else None, epilogue=0)
+        if need_w or (need_x and not fused_dx):
             G = _aggregate(plan, ea_s, gout, Kw, transposed=True)           # G_k = S_k^T gout  [N, Kw*Fo]
             if ctx.selfconn:
                 G[:, K * Fo:] = gout
-            if need_x:
+            if need_x and not fused_dx:
                 dx = ops.gemm_nn(G, weight.transpose(1, 2).contiguous().view(Kw * Fo, Fi), precision=prec)
             if need_w:
                 dw = ops.gemm_tn(x, G, precision=prec).view(Fi, Kw, Fo).permute(1, 0, 2).contiguous()
@@ -106,6 +128,8 @@ class _SpectConvFn(torch.autograd.Function):
         if need_ea:
             if plan.E == 0:
                 dea = torch.zeros_like(ea_s)
+            elif ctx.fused and ops.fused_sddmm_supported(K, Fi, Fo):
+                dea = ops.fused_sddmm(plan.rowptr, plan.col, x, gout, weight[:K].contiguous(), plan.E)
             else:
                 wp = weight[:K].permute(2, 0, 1).reshape(Fo, K * Fi).contiguous()
                 dH = ops.gemm_nn(gout, wp, precision=prec)                   # [N, K*Fi]
