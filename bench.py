@@ -35,7 +35,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="zinc", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="zinc", choices=sorted(WORKLOADS) + ["spectconv_sweep"],
+                    help="zinc (default, BASELINE.json configs[1]) / counting: GNNML3 training; spectconv_sweep: one SpectConv "
+                         "layer fwd+bwd on a 1M-node batch (BASELINE.json configs[4]), reported as HBM GB/s")
+    ap.add_argument("--sweep-nodes", type=int, default=1000000)
+    ap.add_argument("--sweep-f", type=int, default=64)
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU per step (0 = workload default)")
     ap.add_argument("--pool", type=int, default=2048, help="distinct synthetic graphs in the pool")
     ap.add_argument("--ring", type=int, default=6, help="distinct resident batches cycled through (> L2 in total)")
@@ -137,6 +141,78 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def run_sweep(args, local):
+    """Second headline metric of BASELINE.json: SpectConv fwd+bwd achieved HBM GB/s on a 1M-node batch of 30-100-node
+    graphs (K = 10 supports, F -> F).  achieved = SURVEY.md 8d algorithmic bytes (fwd + bwd, every operand once, the
+    [N, K*F] aggregate never credited) / device time of one forward + backward."""
+    from gnn_matlang_b200 import _lib
+    from gnn_matlang_b200.graph import get_plan, set_range_check
+    from gnn_matlang_b200.libs.spect_conv import SpectConv
+    from gnn_matlang_b200.synthetic import GraphPool
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    set_range_check(False)
+    F, K = args.sweep_f, 10
+    pool = GraphPool("sweep", 2048, seed=1, K=K, nfeat=F)
+    rng = np.random.default_rng(3)
+    B = int(args.sweep_nodes / float(pool.n.mean()))
+    hb = pool.draw(rng, B)
+    N, E = hb.x.shape[0], hb.edge_index2.shape[1]
+    torch.manual_seed(0)
+    layer = SpectConv(F, F, K, selfconn=False).to(dev)
+    ei = hb.edge_index2.to(dev)
+    ea = hb.edge_attr2.to(dev).requires_grad_(True)
+    xs = [torch.randn(N, F, device=dev).requires_grad_(True) for _ in range(3)]       # 3 x 256 MB inputs > L2
+    gout = torch.randn(N, F, device=dev)
+    get_plan(ei, N)
+
+    def step(i):
+        x = xs[i % len(xs)]
+        out = layer(x, ei, ea)
+        out.backward(gout)
+        x.grad = None
+        ea.grad = None
+        layer.zero_grad(set_to_none=True)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    from gnn_matlang_b200 import ops
+    ops.profile_start()
+    for i in range(2):
+        step(i)
+    agg = {}
+    for n_, m_, _ in ops.profile_stop():
+        agg[n_] = agg.get(n_, 0.0) + m_ / 2
+    breakdown = {k: round(v, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
+    fwd = 4.0 * (N * F + E * K + E + (N + 1) + K * F * F + F + N * F)
+    bwd = 4.0 * (N * F + N * F + E * K + 2 * E + (N + 1) + N * F + E * K + 2 * K * F * F + F)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = (fwd + bwd) / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "SpectConv fwd+bwd HBM GB/s", "value": ach, "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "spectconv_sweep", "nodes": int(N), "support_entries": int(E), "graphs": int(B), "K": K, "F_in": F,
+                   "F_out": F, "mask": "1-hop", "l2_policy": "3 distinct %d MB inputs cycled" % (N * F * 4 // 1000000)},
+        "roofline": {"kernel": "SpectConv layer fwd+bwd (all launches)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": None, "algorithmic_bytes_fwd": fwd, "algorithmic_bytes_bwd": bwd},
+        "graphs_per_s": B / (ms * 1e-3), "kernel_ms_per_step": breakdown}), flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -144,6 +220,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "spectconv_sweep":
+        if rank == 0:
+            run_sweep(args, local)
         return
 
     import torch.distributed as dist
