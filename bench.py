@@ -275,8 +275,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    th0 = time.perf_counter()
     for i in range(args.steps):
         loss_t = trainer.step(dev_ring[i % args.ring].fresh())
+    host_ms = (time.perf_counter() - th0) * 1e3 / args.steps      # CPU time to ENQUEUE a step (no sync inside the loop)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -395,7 +397,7 @@ def main():
                        "parallelism": "dp%d" % world, "l2_policy": "ring of %d distinct resident batches, %.0f MB in total (> 126 MB L2)" % (args.ring, args.ring * batch_bytes / 1e6),
                        "timed_step": "csr_build + fwd + loss + bwd + (allreduce) + Adam"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "kernel_ms_per_step": breakdown, "final_loss": float(loss_t.item())}), flush=True)
+            "clocks": sampler.summary(), "host_enqueue_ms_per_step": host_ms, "kernel_ms_per_step": breakdown, "final_loss": float(loss_t.item())}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

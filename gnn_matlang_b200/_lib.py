@@ -54,6 +54,12 @@ SIGNATURES = {
     "gnnml3_fused_sddmm_supported": (_i, [_i, _i, _i]),
     "gnnml3_fused_sddmm_workspace_bytes": (_sz, [_i]),
     "gnnml3_fused_sddmm": (_i, [_p, _p, _p, _i64, _i, _p, _i64, _i, _p, _i, _i64, _p, _p, _sz, _p]),
+    "gnnml3_ml3layer_supported": (_i, [_i, _i, _i, _i, _i]),
+    "gnnml3_ml3layer_workspace_bytes": (_sz, [_i64, _i64, _i, _i, _i, _i]),
+    "gnnml3_ml3layer_forward": (_i, [_p, _p, _i64, _i64, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p,
+                                     _i64, _p, _p, _sz, _p]),
+    "gnnml3_ml3layer_backward": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i,
+                                      _p, _i64, _p, _p, _i64, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gnnml3_segment_pool_fwd": (_i, [_p, _i64, _p, _i, _i, _i, _p, _p]),
     "gnnml3_segment_pool_bwd": (_i, [_p, _p, _i, _i, _i, _p, _i64, _p]),
     "gnnml3_spectral_max_nodes": (_i, [_i]),
@@ -95,7 +101,9 @@ def check(rc, what):
 
 
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of the current stream of the current device (raw fast path: torch.cuda.current_stream() builds a Python
+    Stream object per call, ~15 us)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def ptr(t):

@@ -26,6 +26,7 @@ from ..graph import get_plan, sorted_edge_attr
 
 _PRECISIONS = {"fp32": _lib.PREC_3XTF32, "3xtf32": _lib.PREC_3XTF32, "tf32": _lib.PREC_TF32}
 USE_FUSED = os.environ.get("GNNML3_NO_FUSED", "0") != "1"
+USE_LAYER_API = os.environ.get("GNNML3_NO_LAYER_API", "0") != "1"
 
 
 def _use_fused(precision):
@@ -214,6 +215,18 @@ class _ML3LayerFn(torch.autograd.Function):
         N, Fi = x.shape
         K, _, Fo = wconv.shape
         G = 0 if w11 is None else w11.size(0)
+        ctx.composite = False
+        if (_use_fused(precision) and USE_LAYER_API and N > 0 and plan.E > 0 and (fused_edge or w1 is None)
+                and ops.ml3layer_supported(K, Fi, Fo, G, fused_edge)):
+            # the whole layer in ONE library call (layer_api.cu): same kernels as below, a fraction of the host time
+            xa = ops.aligned_rows(x)
+            ws4 = tuple(w.contiguous() for w in (w1, w2, w3, w4)) if fused_edge else None
+            gates = (w11.contiguous(), b11.contiguous(), w12.contiguous(), b12.contiguous()) if G > 0 else None
+            y, aux, ea2 = ops.ml3layer_forward(plan, xa, ea_s, ws4, wconv, bconv.contiguous() if bconv is not None else None, gates)
+            ctx.plan, ctx.fused_edge, ctx.precision, ctx.G = plan, fused_edge, precision, G
+            ctx.has_bias, ctx.fused, ctx.composite = bconv is not None, True, True
+            ctx.save_for_backward(xa, ea_s, ea2, y, aux, w1, w2, w3, w4, wconv, w11, w12)
+            return y
         if fused_edge:
             w1, w2, w3, w4 = w1.contiguous(), w2.contiguous(), w3.contiguous(), w4.contiguous()
             ea2 = ops.edge_mlp_fwd(ea_s, None, w1, w2, w3, w4)
@@ -256,6 +269,12 @@ class _ML3LayerFn(torch.autograd.Function):
         N, Fi = x.shape
         K, _, Fo = wconv.shape
         need = ctx.needs_input_grad
+        if ctx.composite and N > 0:
+            gy = gy if gy.stride(1) == 1 else gy.contiguous()
+            ws4 = (w1, w2, w3, w4) if ctx.fused_edge else None
+            dx, dea, dws, dwc, dbc, dw11, db11, dw12, db12 = ops.ml3layer_backward(
+                plan, x, ea_s, ea2, ws4, wconv, (w11, w12) if G > 0 else None, pre, aux, gy, need[0], need[1], ctx.has_bias)
+            return (dx, dea, dws[0], dws[1], dws[2], dws[3], dwc, dbc, dw11, db11, dw12, db12, None, None, None)
         gy = gy.contiguous()
         Gp = torch.empty(N, K * Fo + 2 * G, dtype=torch.float32, device=x.device)
         if ctx.fused:

@@ -12,6 +12,26 @@ from . import _lib
 _workspaces = {}
 
 
+class _NullCtx(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _on(device):
+    """Context that makes ``device`` current -- a no-op object when it already is (torch.cuda.device() costs ~10 us of
+    host time per call, and every training step makes ~90 library calls)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
+
+
 def _ws(device, nbytes, tag="main"):
     """Grow-only per-device scratch buffer (stream-ordered reuse on the current stream)."""
     key = (device.index, tag)
@@ -62,7 +82,7 @@ def csr_build(edge_index, num_nodes, check_range=True):
     flag = torch.zeros(1, **i32)
     nbytes = lib.gnnml3_csr_workspace_bytes(E, N)
     ws = _ws(dev, nbytes)
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib.gnnml3_csr_build(_lib.ptr(ei), E, N, _lib.ptr(out["rowptr"]), _lib.ptr(out["col"]), _lib.ptr(out["perm"]),
                                   _lib.ptr(out["rowptrT"]), _lib.ptr(out["colT"]), _lib.ptr(out["permT"]),
                                   _lib.ptr(flag), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
@@ -77,7 +97,7 @@ def gather_rows(src, perm):
     src = _f32c(src, "src")
     rows, width = perm.numel(), src.size(1)
     out = torch.empty(rows, width, dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         _lib.check(lib.gnnml3_gather_rows(_lib.ptr(src), _lib.ptr(perm), rows, width, _lib.ptr(out), _lib.stream_ptr()),
                    "gnnml3_gather_rows")
     return out
@@ -88,7 +108,7 @@ def scatter_rows(src, perm):
     src = _f32c(src, "src")
     rows, width = perm.numel(), src.size(1)
     out = torch.empty(rows, width, dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         _lib.check(lib.gnnml3_scatter_rows(_lib.ptr(src), _lib.ptr(perm), rows, width, _lib.ptr(out), _lib.stream_ptr()),
                    "gnnml3_scatter_rows")
     return out
@@ -105,7 +125,7 @@ def spmm_k(rowptr, col, eperm, ea, x, out=None):
         out = torch.empty(N, K * F, dtype=torch.float32, device=x.device)
     if N == 0:
         return out
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(lib.gnnml3_spmm_k(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(ea), _lib.ptr(x), _ld(x),
                                      N, K, F, _lib.ptr(out), _ld(out), _lib.stream_ptr()), "gnnml3_spmm_k")
     return out
@@ -120,7 +140,7 @@ def sddmm_k(rowptr, col, eperm, x, g, K, E):
     dea = torch.empty(E, K, dtype=torch.float32, device=x.device)
     if N == 0 or E == 0:
         return dea
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(lib.gnnml3_sddmm_k(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(x), _ld(x), _lib.ptr(g),
                                       _ld(g), N, K, F, _lib.ptr(dea), _lib.stream_ptr()), "gnnml3_sddmm_k")
     return dea
@@ -146,7 +166,7 @@ def gemm_nn_tc(A, B, bias=None, epilogue=_lib.EPI_NONE, out=None, chunk_kblocks=
     if bias is not None:
         bias = _f32c(bias, "bias")
     ws = _ws(A.device, lib.gnnml3_gemm_nn_tc_workspace_bytes(Nc, Kc), tag="tc")
-    with torch.cuda.device(A.device):
+    with _on(A.device):
         _lib.check(lib.gnnml3_gemm_nn_tc(_lib.ptr(A), _ld(A), _lib.ptr(B), _ld(B), _lib.ptr(bias), _lib.ptr(out), _ld(out),
                                          M, Nc, Kc, epilogue, chunk_kblocks, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                    "gnnml3_gemm_nn_tc")
@@ -172,7 +192,7 @@ def gemm_nn(A, B, bias=None, precision=_lib.PREC_3XTF32, epilogue=_lib.EPI_NONE,
         return out
     if bias is not None:
         bias = _f32c(bias, "bias")
-    with torch.cuda.device(A.device):
+    with _on(A.device):
         _lib.check(lib.gnnml3_gemm_nn(_lib.ptr(A), _ld(A), _lib.ptr(B), _ld(B), _lib.ptr(bias), _lib.ptr(out),
                                       _ld(out), M, Nc, Kc, precision, epilogue, _lib.stream_ptr()), "gnnml3_gemm_nn")
     return out
@@ -190,7 +210,7 @@ def gemm_tn(A, B, precision=_lib.PREC_3XTF32):
         return out.zero_()
     nbytes = lib.gnnml3_gemm_tn_workspace_bytes(M, Ka, Nb)
     ws = _ws(A.device, nbytes)
-    with torch.cuda.device(A.device):
+    with _on(A.device):
         _lib.check(lib.gnnml3_gemm_tn(_lib.ptr(A), _ld(A), _lib.ptr(B), _ld(B), _lib.ptr(out), _ld(out), M, Ka,
                                       Nb, precision, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_gemm_tn")
     return out
@@ -205,7 +225,7 @@ def colsum(A):
         return out.zero_()
     nbytes = lib.gnnml3_colsum_workspace_bytes(M, Nc)
     ws = _ws(A.device, nbytes)
-    with torch.cuda.device(A.device):
+    with _on(A.device):
         _lib.check(lib.gnnml3_colsum(_lib.ptr(A), _ld(A), M, Nc, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
                                      _lib.stream_ptr()), "gnnml3_colsum")
     return out
@@ -223,7 +243,7 @@ def edge_mlp_fwd(ea, eperm, w1, w2, w3, w4):
     E, K = ea.shape
     Kout = w4.size(0)
     out = torch.empty(E, Kout, dtype=torch.float32, device=ea.device)
-    with torch.cuda.device(ea.device):
+    with _on(ea.device):
         _lib.check(lib.gnnml3_edge_mlp_fwd(_lib.ptr(ea), _lib.ptr(eperm), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3), _lib.ptr(w4),
                                            E, K, Kout, _lib.ptr(out), _lib.stream_ptr()), "gnnml3_edge_mlp_fwd")
     return out
@@ -241,7 +261,7 @@ def edge_mlp_bwd(ea, eperm, gout, w1, w2, w3, w4, need_dea):
     dw = [torch.empty_like(w) for w in (w1, w2, w3, w4)]
     nbytes = lib.gnnml3_edge_mlp_bwd_workspace_bytes(E, K)
     ws = _ws(dev, nbytes)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gnnml3_edge_mlp_bwd(_lib.ptr(ea), _lib.ptr(eperm), _lib.ptr(gout), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3),
                                            _lib.ptr(w4), E, K, Kout, _lib.ptr(dea), _lib.ptr(dw[0]), _lib.ptr(dw[1]),
                                            _lib.ptr(dw[2]), _lib.ptr(dw[3]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
@@ -253,7 +273,7 @@ def ml3_act_fwd(pre, Fo, G):
     lib = _lib.load()
     N = pre.size(0)
     y = torch.empty(N, Fo + G, dtype=torch.float32, device=pre.device)
-    with torch.cuda.device(pre.device):
+    with _on(pre.device):
         _lib.check(lib.gnnml3_ml3_act_fwd(_lib.ptr(pre), _ld(pre), N, Fo, G, _lib.ptr(y), _ld(y), _lib.stream_ptr()),
                    "gnnml3_ml3_act_fwd")
     return y
@@ -271,7 +291,7 @@ def ml3_act_bwd(pre, gy, Fo, G, gate_out=None):
     gpre = torch.empty(N, ld4, dtype=torch.float32, device=pre.device)[:, :Fo + 2 * G]
     csum = torch.empty(Fo + 2 * G, dtype=torch.float32, device=pre.device)
     ws = _ws(pre.device, lib.gnnml3_ml3_act_bwd_workspace_bytes(N, Fo, G))
-    with torch.cuda.device(pre.device):
+    with _on(pre.device):
         _lib.check(lib.gnnml3_ml3_act_bwd(_lib.ptr(pre), _ld(pre), _lib.ptr(gy), _ld(gy), N, Fo, G, _lib.ptr(gpre),
                                           _ld(gpre), _lib.ptr(gate_out) if gate_out is not None else None,
                                           _ld(gate_out) if gate_out is not None else 0, _lib.ptr(csum), _lib.ptr(ws),
@@ -332,7 +352,7 @@ def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mod
     _prof["last_bytes"] = 4.0 * (N * F + (N * Fs if (self_mode and S.data_ptr() != x.data_ptr()) else 0) + E * K + E * (2 if eperm is not None else 1)
                                  + (N + 1) + K * F * Nc + Fs * Ns + Nc + N * W + (N * 2 * G if self_mode == 1 else 0))
     ws = _ws(dev, lib.gnnml3_fused_workspace_bytes(K, F, Nc, self_mode), tag="fused")
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gnnml3_fused_agg_proj(
             _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(ea), K, K, _lib.ptr(x), _ld(x), F,
             _lib.ptr(S) if self_mode else None, _ld(S) if self_mode else 0, Fs, self_mode, _lib.ptr(Bmain), _ld(Bmain),
@@ -353,7 +373,7 @@ def ml3_act_bwd_y(y, aux, gy, Fo, G):
     gpre = torch.empty(N, ldg, dtype=torch.float32, device=y.device)
     csum = torch.empty(Fo + 2 * G, dtype=torch.float32, device=y.device)
     ws = _ws(y.device, lib.gnnml3_ml3_act_bwd_workspace_bytes(N, Fo, G))
-    with torch.cuda.device(y.device):
+    with _on(y.device):
         _lib.check(lib.gnnml3_ml3_act_bwd_y(_lib.ptr(y), _ld(y), _lib.ptr(aux), 2 * G, _lib.ptr(gy), _ld(gy), N, Fo, G,
                                             _lib.ptr(gpre), ldg, _lib.ptr(csum), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                    "gnnml3_ml3_act_bwd_y")
@@ -373,11 +393,76 @@ def fused_sddmm(rowptr, col, x, gc, W, E):
     N = rowptr.numel() - 1
     dea = torch.empty(E, K, dtype=torch.float32, device=x.device)
     ws = _ws(x.device, lib.gnnml3_fused_sddmm_workspace_bytes(K), tag="fused_sddmm")
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(lib.gnnml3_fused_sddmm(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(x), _ld(x), Fi, _lib.ptr(gc), _ld(gc), Fo,
                                           _lib.ptr(W), K, N, _lib.ptr(dea), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                    "gnnml3_fused_sddmm")
     return dea
+
+
+def ml3layer_supported(K, Fi, Fo, G, learnedge):
+    return bool(_lib.load().gnnml3_ml3layer_supported(int(K), int(Fi), int(Fo), int(G), int(bool(learnedge))))
+
+
+def ml3layer_forward(plan, x, ea_s, ws4, wconv, bconv, gates):
+    """Whole ML3Layer forward in one library call (gnnml3_ml3layer_forward).  ``ws4`` = (w1, w2, w3, w4) or None,
+    ``gates`` = (w11, b11, w12, b12) or None.  -> (y [N, Fo+G], aux [N, 2G] | None, ea2 [E, K] | None)"""
+    lib = _lib.load()
+    N, Fi = x.shape
+    E, K = ea_s.shape
+    Fo = wconv.size(2)
+    G = gates[0].size(0) if gates is not None else 0
+    dev = x.device
+    W = Fo + G
+    ldy = (W + 3) // 4 * 4
+    y = torch.empty(N, ldy, dtype=torch.float32, device=dev)
+    if ldy != W:
+        y[:, W:].zero_()
+    aux = torch.empty(N, 2 * G, dtype=torch.float32, device=dev) if G > 0 else None
+    ea2 = torch.empty(E, K, dtype=torch.float32, device=dev) if ws4 is not None else None
+    ws = _ws(dev, lib.gnnml3_ml3layer_workspace_bytes(N, E, K, Fi, Fo, G), tag="layer")
+    p = _lib.ptr
+    w = ws4 if ws4 is not None else (None,) * 4
+    g = gates if gates is not None else (None,) * 4
+    with _on(dev):
+        _lib.check(lib.gnnml3_ml3layer_forward(p(plan.rowptr), p(plan.col), N, E, p(x), _ld(x), Fi, p(ea_s), K, p(w[0]), p(w[1]), p(w[2]),
+                                               p(w[3]), p(wconv), p(bconv), Fo, p(g[0]), p(g[1]), p(g[2]), p(g[3]), G, p(ea2), p(y), ldy,
+                                               p(aux), p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_forward")
+    return y[:, :W], aux, ea2
+
+
+def ml3layer_backward(plan, x, ea_s, ea2, ws4, wconv, gates_w, y, aux, gy, need_dx, need_dea, has_bias):
+    """Whole ML3Layer backward in one library call (gnnml3_ml3layer_backward).
+    -> dx, dea, (dw1..dw4), dwconv, dbconv, dw11, db11, dw12, db12 (None where not applicable)"""
+    lib = _lib.load()
+    N, Fi = x.shape
+    E, K = ea_s.shape
+    Fo = wconv.size(2)
+    G = gates_w[0].size(0) if gates_w is not None else 0
+    dev = x.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    lddx = (Fi + 3) // 4 * 4
+    dx = torch.empty(N, lddx, **f32) if need_dx else None
+    dea = torch.empty(E, K, **f32) if need_dea else None
+    dws = [torch.empty_like(t) for t in ws4] if ws4 is not None else [None] * 4
+    dwc = torch.empty_like(wconv)
+    dbias = torch.empty(Fo + 2 * G, **f32)
+    dw11 = torch.empty(G, Fi, **f32) if G > 0 else None
+    dw12 = torch.empty(G, Fi, **f32) if G > 0 else None
+    ws = _ws(dev, lib.gnnml3_ml3layer_workspace_bytes(N, E, K, Fi, Fo, G), tag="layer")
+    p = _lib.ptr
+    w = ws4 if ws4 is not None else (None,) * 4
+    gw = gates_w if gates_w is not None else (None, None)
+    with _on(dev):
+        _lib.check(lib.gnnml3_ml3layer_backward(
+            p(plan.rowptr), p(plan.col), p(plan.rowptrT), p(plan.colT), p(plan.permT), N, E, p(x), _ld(x), Fi, p(ea_s), p(ea2), K,
+            p(w[0]), p(w[1]), p(w[2]), p(w[3]), p(wconv), Fo, p(gw[0]), p(gw[1]), G, p(y), _ld(y), p(aux), p(gy), _ld(gy),
+            int(need_dx), int(need_dea), p(dx), lddx, p(dea), p(dws[0]), p(dws[1]), p(dws[2]), p(dws[3]), p(dwc), p(dbias), p(dw11),
+            p(dw12), p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_backward")
+    dbc = dbias[:Fo] if has_bias else None
+    db11 = dbias[Fo:Fo + G] if G > 0 else None
+    db12 = dbias[Fo + G:] if G > 0 else None
+    return (dx[:, :Fi] if need_dx else None), dea, dws, dwc, dbc, dw11, db11, dw12, db12
 
 
 def segment_pool_fwd(x, graph_ptr, mean):
@@ -385,7 +470,7 @@ def segment_pool_fwd(x, graph_ptr, mean):
     x = _f32c(x, "x")
     B, F = graph_ptr.numel() - 1, x.size(1)
     out = torch.empty(B, F, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(lib.gnnml3_segment_pool_fwd(_lib.ptr(x), _ld(x), _lib.ptr(graph_ptr), B, F, int(mean), _lib.ptr(out),
                                                _lib.stream_ptr()), "gnnml3_segment_pool_fwd")
     return out
@@ -396,7 +481,7 @@ def segment_pool_bwd(gout, graph_ptr, mean, N):
     gout = _f32c(gout, "gout")
     B, F = gout.shape
     gx = torch.empty(N, F, dtype=torch.float32, device=gout.device)
-    with torch.cuda.device(gout.device):
+    with _on(gout.device):
         _lib.check(lib.gnnml3_segment_pool_bwd(_lib.ptr(gout), _lib.ptr(graph_ptr), B, F, int(mean), _lib.ptr(gx), _ld(gx),
                                                _lib.stream_ptr()), "gnnml3_segment_pool_bwd")
     return gx
@@ -440,6 +525,6 @@ def _instrument(name, fn):
 
 
 for _n in ("csr_build", "gather_rows", "scatter_rows", "spmm_k", "sddmm_k", "gemm_nn_tc", "gemm_nn", "gemm_tn", "colsum", "edge_mlp_fwd",
-           "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "ml3_act_bwd_y", "fused_agg_proj", "fused_sddmm", "segment_pool_fwd",
+           "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "ml3_act_bwd_y", "fused_agg_proj", "fused_sddmm", "ml3layer_forward", "ml3layer_backward", "segment_pool_fwd",
            "segment_pool_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

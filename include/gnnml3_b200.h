@@ -175,6 +175,34 @@ GNNML3_API int gnnml3_fused_sddmm(const int32_t* rowptr, const int32_t* col, con
                        size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Whole-layer entry points (layer_api.cu): ONE call enqueues every kernel of an ML3Layer forward
+ * (libs/spect_conv.py:204-212: edge MLP -> SpectConv -> ReLU || tanh*tanh gates) or of its backward, on a caller-provided
+ * workspace (gnnml3_ml3layer_workspace_bytes).  Same kernels and arithmetic as composing the single-kernel entry points;
+ * the point is the host cost (one call instead of ~30 small operations per layer and direction).
+ *   forward : ea_s [E,K] dst-sorted edge features; w1..w4 = fc1_1..fc1_4.weight (NULL: learnedge = False, ea2 unused);
+ *             wconv [K,Fi,Fo], bconv [Fo] (nullable); w11,b11,w12,b12 = fc11/fc12 (NULL iff G == 0);
+ *             outputs ea2 [E,K], y [N, ldy >= Fo+G], aux [N, 2G] (tanh factors, saved for the backward).
+ *   backward: gy [N, ldgy]; outputs dx [N, lddx] (if need_dx), dea [E,K] (if need_dea), dw1..dw4, dwconv [K,Fi,Fo],
+ *             dbias [Fo + 2G] = (d bconv | d b11 | d b12), dw11/dw12 [G,Fi].
+ * x rows must be 16-byte aligned (ldx % 4 == 0).  gnnml3_ml3layer_supported tells whether a shape is covered.
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API int gnnml3_ml3layer_supported(int K, int Fi, int Fo, int G, int learnedge);
+GNNML3_API size_t gnnml3_ml3layer_workspace_bytes(int64_t N, int64_t E, int K, int Fi, int Fo, int G);
+GNNML3_API int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col, int64_t N, int64_t E, const float* x, int64_t ldx,
+                            int Fi, const float* ea_s, int K, const float* w1, const float* w2, const float* w3,
+                            const float* w4, const float* wconv, const float* bconv, int Fo, const float* w11,
+                            const float* b11, const float* w12, const float* b12, int G, float* ea2, float* y,
+                            int64_t ldy, float* aux, void* workspace, size_t workspace_bytes, void* stream);
+GNNML3_API int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* rowptrT, const int32_t* colT,
+                             const int32_t* permT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
+                             const float* ea_s, const float* ea2, int K, const float* w1, const float* w2, const float* w3,
+                             const float* w4, const float* wconv, int Fo, const float* w11, const float* w12, int G,
+                             const float* y, int64_t ldy, const float* aux, const float* gy, int64_t ldgy, int need_dx,
+                             int need_dea, float* dx, int64_t lddx, float* dea, float* dw1, float* dw2, float* dw3,
+                             float* dw4, float* dwconv, float* dbias, float* dw11, float* dw12, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Readout: PyG global_add_pool (mean = 0) / global_mean_pool (mean = 1) over contiguous node ranges
  * graph_ptr [B+1] (graph b owns nodes graph_ptr[b] .. graph_ptr[b+1]-1, as produced by batching).
  * --------------------------------------------------------------------------------------------------- */
