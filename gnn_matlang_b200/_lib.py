@@ -47,10 +47,12 @@ SIGNATURES = {
     "gnnml3_ml3_act_bwd_y": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i, _i, _p, _i64, _p, _p, _sz, _p]),
     "gnnml3_fused_debug_counters": (_i, [_p, _i]),
     "gnnml3_fused_set_mode": (_i, [_i]),
+    "gnnml3_fused_profile": (_i, [_i]),
+    "gnnml3_fused_profile_fetch": (_i, [_p, _i]),
     "gnnml3_fused_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "gnnml3_fused_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "gnnml3_fused_agg_proj": (_i, [_p, _p, _p, _p, _i, _i, _p, _i64, _i, _p, _i64, _i, _i, _p, _i64, _p, _i64, _i, _p, _p,
-                                   _i64, _i, _p, _i64, _p, _i64, _i, _i, _p, _sz, _p]),
+                                   _i64, _i, _p, _i64, _p, _i64, _i, _i, _p, _i64, _p, _sz, _p]),
     "gnnml3_fused_sddmm_supported": (_i, [_i, _i, _i]),
     "gnnml3_fused_sddmm_workspace_bytes": (_sz, [_i]),
     "gnnml3_fused_sddmm": (_i, [_p, _p, _p, _i64, _i, _p, _i64, _i, _p, _i, _i64, _p, _p, _sz, _p]),

@@ -24,6 +24,8 @@
 // accumulates into the same output columns.  SpectConv(selfconn=True) uses that mode in the forward, too.
 #include "tc_common.cuh"
 
+#include <vector>
+
 // cycle counters of the warp roles (gnnml3_fused_debug_counters): compiled in only with -DFL_PROFILE, they cost issue
 // slots and registers in the single-thread control loops that pace the whole kernel
 #ifdef FL_PROFILE
@@ -67,6 +69,8 @@ struct FLParams {
     int64_t ldaux;
     int G;
     int epi;                // 0 plain (+bias) | 1 ml3: relu on the main columns, gating on the self columns
+    float* hout;            // optional copy of the aggregate: [N, ldh], support k at column k * 32 * nfh (zero padded), self block behind
+    int64_t ldh;
     unsigned long long* dbg; // optional cycle counters (GNNML3_FUSED_DEBUG=1): see gnnml3_fused_debug_counters
 };
 
@@ -690,6 +694,14 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                             }
                         }
                     }
+                    if (P.hout && row < P.N) {           // side output for the weight-gradient contraction of the backward
+                        float* hr = P.hout + row * P.ldh + (int64_t)k0 * 32 * P.nfh + fh * 32 + g * 4;
+#pragma unroll
+                        for (int k = 0; k < KT; ++k) {
+                            st_na4(hr + k * 32 * P.nfh, make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]));
+                            st_na4(hr + k * 32 * P.nfh + 16, make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]));
+                        }
+                    }
                     // hand the KT finished k-blocks to the tensor core
                     __syncwarp();
                     FL_CNT(c_gather += clock64() - cg0;)
@@ -727,6 +739,11 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         const float4 t = ldg4(sr + 16 + g * 4);
                         sv[4] = t.x; sv[5] = t.y; sv[6] = t.z; sv[7] = t.w;
                     }
+                }
+                if (P.hout && row < P.N) {
+                    float* hr = P.hout + row * P.ldh + (int64_t)P.K * 32 * P.nfh + g * 4;
+                    st_na4(hr, make_float4(sv[0], sv[1], sv[2], sv[3]));
+                    st_na4(hr + 16, make_float4(sv[4], sv[5], sv[6], sv[7]));
                 }
                 const uint32_t s = st_i;
                 mbar_wait(empty + s, st_ph);
@@ -848,6 +865,41 @@ extern "C" size_t gnnml3_fused_workspace_bytes(int K, int F, int Nc, int self_mo
 constexpr size_t FL_SMEM_MAX = 227 * 1024;                                              // opt-in limit per CTA on sm_100
 constexpr size_t FL_SMEM_FIXED = 2 * FL_XCH * sizeof(float) + 1024 /*alignment slack*/ + 256 /*barriers*/ + 128 /*slot alignment*/;
 
+// Per-launch device timing for bench.py's roofline: CUDA events recorded on the launching stream around the kernel
+// (gnnml3_fused_profile / gnnml3_fused_profile_fetch).  Off by default; not thread-safe (a measurement aid).
+struct FLProfRec {
+    cudaEvent_t a, b;
+    double meta[9];      // N, K, F, Nc, Fs, self_mode, Ns, G, has_perm
+};
+static bool g_fl_prof_on = false;
+static std::vector<FLProfRec> g_fl_prof;
+
+extern "C" int gnnml3_fused_profile(int enable) {
+    for (auto& r : g_fl_prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_fl_prof.clear();
+    g_fl_prof_on = enable != 0;
+    return GNNML3_OK;
+}
+
+// out [max][10]: milliseconds, N, K, F, Nc, Fs, self_mode, Ns, G, has_perm of every fused launch since profiling was
+// enabled; synchronises the device.  Returns the number of records written.
+extern "C" int gnnml3_fused_profile_fetch(double* out, int max) {
+    cudaDeviceSynchronize();
+    int n = 0;
+    for (auto& r : g_fl_prof) {
+        if (n >= max) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        out[n * 10] = ms;
+        for (int i = 0; i < 9; ++i) out[n * 10 + 1 + i] = r.meta[i];
+        ++n;
+    }
+    return n;
+}
+
 template <int KT, int BNH, int NAGG, bool RES>
 static int fl_launch2(const CUtensorMap& mW, FLParams& P, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
@@ -857,7 +909,20 @@ static int fl_launch2(const CUtensorMap& mW, FLParams& P, size_t smem, cudaStrea
         configured = FL_SMEM_MAX;
     }
     const int grid = P.n_tiles < kNumSMs ? P.n_tiles : kNumSMs;
+    FLProfRec rec;
+    if (g_fl_prof_on) {
+        cudaEventCreate(&rec.a);
+        cudaEventCreate(&rec.b);
+        const double m[9] = {(double)P.N, (double)P.K, (double)P.F, (double)P.Nc, (double)P.Fs, (double)P.self_mode,
+                             (double)(P.self_mode == 1 ? 2 * P.G : 0), (double)P.G, P.eperm ? 1.0 : 0.0};
+        for (int i = 0; i < 9; ++i) rec.meta[i] = m[i];
+        cudaEventRecord(rec.a, st);
+    }
     k_fused_agg_proj<KT, BNH, NAGG, RES><<<grid, 32 * (FL_CTRL_WARPS + NAGG), smem, st>>>(mW, P);
+    if (g_fl_prof_on) {
+        cudaEventRecord(rec.b, st);
+        g_fl_prof.push_back(rec);
+    }
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
@@ -960,7 +1025,7 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
                                      int Fs, int self_mode, const float* Bmain, int64_t ldb, const float* Bself,
                                      int64_t ldbs, int Ns, const float* bias, const float* bias_s, int64_t N, int Nc,
                                      float* out, int64_t ldo, float* aux, int64_t ldaux, int G, int epilogue,
-                                     void* workspace, size_t workspace_bytes, void* stream_) {
+                                     float* hout, int64_t ldh, void* workspace, size_t workspace_bytes, void* stream_) {
     GNNML3_REQUIRE(N > 0 && N < (1ll << 31) - 256, "fused_agg_proj: bad N");
     GNNML3_REQUIRE(rowptr && col && ea && X && Bmain && out && workspace, "fused_agg_proj: NULL pointer");
     GNNML3_REQUIRE(gnnml3_fused_supported(K, Kstride, F, Nc, Fs, self_mode, Ns), "fused_agg_proj: unsupported shape "
@@ -973,6 +1038,9 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
     GNNML3_REQUIRE(self_mode != 1 || (epilogue == 1 && aux && G >= 1 && G <= 16 && Ns == 2 * G),
                    "fused_agg_proj: gate columns need the ML3 epilogue, aux and Ns == 2G <= 32");
     GNNML3_REQUIRE(ldo >= Nc + (self_mode == 1 ? G : 0), "fused_agg_proj: ldo too small");
+    GNNML3_REQUIRE(hout == nullptr || (ldh % 4 == 0 && (uintptr_t)hout % 16 == 0 && g_fl_slot_mode == 0 &&
+                                       ldh >= (int64_t)(K + (self_mode != 0 ? 1 : 0)) * 32 * cdiv(F, 32)),
+                   "fused_agg_proj: hout needs the default aggregator mode and 16-byte aligned rows of (K [+1]) * 32 * ceil(F/32) floats");
     if (workspace_bytes < gnnml3_fused_workspace_bytes(K, F, Nc, self_mode))
         return set_err(GNNML3_ERR_WORKSPACE, "fused_agg_proj: workspace too small");
     cudaStream_t st = (cudaStream_t)stream_;
@@ -999,6 +1067,7 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
     P.N = N; P.n_tiles = 0; P.nfh = nfh; P.nkb_main = nkb_main; P.nstages = 0; P.pf_rows = g_fl_pf_rows; P.slot_cap = 0;
     P.bias = bias; P.bias_s = bias_s; P.out = out; P.ldo = ldo; P.Nc = Nc; P.aux = aux; P.ldaux = ldaux; P.G = G;
     P.epi = epilogue;
+    P.hout = hout; P.ldh = ldh;
     if (g_fl_debug && !g_fl_dbg) {
         GNNML3_CUDA(cudaMalloc(&g_fl_dbg, 16 * sizeof(unsigned long long)));
         GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 16 * sizeof(unsigned long long)));

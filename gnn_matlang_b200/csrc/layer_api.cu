@@ -49,20 +49,20 @@ __global__ void k_copy_block(const float* __restrict__ src, int64_t lds, float* 
 }
 
 // dcat [Fi, K*Fo + 2G] = x^T [G_0 .. G_{K-1} | g1 | g2]  ->  dW [K, Fi, Fo], dW11 [G, Fi], dW12 [G, Fi]
-__global__ void k_unpack_dw(const float* __restrict__ dcat, int K, int Fi, int Fo, int G, float* __restrict__ dw, float* __restrict__ dw11,
-                            float* __restrict__ dw12) {
-    const int ld = K * Fo + 2 * G;
+__global__ void k_unpack_dw(const float* __restrict__ dcat, int K, int Fi, int Fo, int G, int pitch, float* __restrict__ dw,
+                            float* __restrict__ dw11, float* __restrict__ dw12) {
+    const int ld = K * pitch + 2 * G;          // support k occupies columns [k * pitch, k * pitch + Fo)
     const int t1 = K * Fi * Fo, t2 = G * Fi;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < t1 + 2 * t2; idx += gridDim.x * blockDim.x) {
         if (idx < t1) {
             const int o = idx % Fo, i = (idx / Fo) % Fi, k = idx / (Fo * Fi);
-            dw[idx] = __ldg(dcat + (int64_t)i * ld + k * Fo + o);
+            dw[idx] = __ldg(dcat + (int64_t)i * ld + k * pitch + o);
         } else if (idx < t1 + t2) {
             const int j = idx - t1, g = j / Fi, i = j % Fi;
-            dw11[j] = __ldg(dcat + (int64_t)i * ld + K * Fo + g);
+            dw11[j] = __ldg(dcat + (int64_t)i * ld + K * pitch + g);
         } else {
             const int j = idx - t1 - t2, g = j / Fi, i = j % Fi;
-            dw12[j] = __ldg(dcat + (int64_t)i * ld + K * Fo + G + g);
+            dw12[j] = __ldg(dcat + (int64_t)i * ld + K * pitch + G + g);
         }
     }
 }
@@ -103,9 +103,12 @@ static LayerWs layer_ws(int64_t N, int64_t E, int K, int Fi, int Fo, int G) {
     w.act = off; off += a256(gnnml3_ml3_act_bwd_workspace_bytes(N, Fo, G));
     w.wT = off; off += a256((size_t)K * Fo * Fi * 4);
     w.ws2 = off; off += a256((size_t)2 * G * Fi * 4 + 4);
-    w.Gp = off; off += a256((size_t)N * (K * Fo + 2 * G) * 4);
-    w.tn = off; off += a256(gnnml3_gemm_tn_workspace_bytes(N, Fi, K * Fo + 2 * G));
-    w.dcat = off; off += a256((size_t)Fi * (K * Fo + 2 * G) * 4);
+    w.Gp = off; off += a256((size_t)N * ((K + 1) * 32) * 4);
+    {   // the split count of gemm_tn depends on the column count: size for both layouts of G' (pitch 32 / pitch Fo)
+        const size_t t1 = gnnml3_gemm_tn_workspace_bytes(N, Fi, K * 32 + 2 * G), t2 = gnnml3_gemm_tn_workspace_bytes(N, Fi, K * Fo + 2 * G);
+        w.tn = off; off += a256(t1 > t2 ? t1 : t2);
+    }
+    w.dcat = off; off += a256((size_t)Fi * (K * 32 + 2 * G) * 4);
     w.dea2 = off; off += a256((size_t)E * K * 4 + 4);
     w.sd = off; off += a256(gnnml3_fused_sddmm_workspace_bytes(K));
     w.emlp = off; off += a256(gnnml3_edge_mlp_bwd_workspace_bytes(E, K));
@@ -143,7 +146,7 @@ extern "C" int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col
         GNNML3_LAUNCH_CHECK();
     }
     return gnnml3_fused_agg_proj(rowptr, col, nullptr, eaw, K, K, x, ldx, Fi, G > 0 ? x : nullptr, ldx, G > 0 ? Fi : 0, G > 0 ? 1 : 0, wconv,
-                                 Fo, wg, 2 * G, 2 * G, bconv, bg, N, Fo, y, ldy, aux, 2 * G, G, 1, ws + w.fused, w.wg - w.fused, stream);
+                                 Fo, wg, 2 * G, 2 * G, bconv, bg, N, Fo, y, ldy, aux, 2 * G, G, 1, nullptr, 0, ws + w.fused, w.wg - w.fused, stream);
 }
 
 extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* rowptrT, const int32_t* colT,
@@ -170,24 +173,38 @@ extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* co
     float* ws2 = (float*)(ws + w.ws2);
     k_pack_bwd<<<cdiv((int64_t)K * Fo * Fi + 2 * G * Fi, 256), 256, 0, st>>>(wconv, w11, w12, K, Fi, Fo, G, wT, ws2);
     GNNML3_LAUNCH_CHECK();
-    if (need_dx) {
+    // weight gradients: x^T [S_0^T gc .. S_{K-1}^T gc | g1 | g2].  When dx is needed the fused dx kernel leaves the aggregate
+    // behind (pitch 32 per support, gate block at K * 32), so no separate SpMM runs; otherwise (first layer) SpMM builds it.
+    float* Gp = (float*)(ws + w.Gp);
+    float* dcat = (float*)(ws + w.dcat);
+    int64_t ldG;
+    int pitch;
+    if (need_dx && gnnml3_fused_set_mode(-1) == 0) {          // (the side output exists in the default aggregator mode only)
+        pitch = 32;
+        ldG = (int64_t)(K + (G > 0 ? 1 : 0)) * 32;
         if ((rc = gnnml3_fused_agg_proj(rowptrT, colT, permT, eaw, K, K, gpre, w.ldg, Fo, G > 0 ? gpre + Fo4 : nullptr, w.ldg, 2 * G,
                                         G > 0 ? 2 : 0, wT, Fi, G > 0 ? ws2 : nullptr, Fi, 0, nullptr, nullptr, N, Fi, dx, lddx, nullptr, 0, 0,
-                                        0, ws + w.fused, w.wg - w.fused, stream)))
+                                        0, Gp, ldG, ws + w.fused, w.wg - w.fused, stream)))
             return rc;
+    } else {
+        if (need_dx) {
+            if ((rc = gnnml3_fused_agg_proj(rowptrT, colT, permT, eaw, K, K, gpre, w.ldg, Fo, G > 0 ? gpre + Fo4 : nullptr, w.ldg, 2 * G,
+                                            G > 0 ? 2 : 0, wT, Fi, G > 0 ? ws2 : nullptr, Fi, 0, nullptr, nullptr, N, Fi, dx, lddx, nullptr, 0,
+                                            0, 0, nullptr, 0, ws + w.fused, w.wg - w.fused, stream)))
+                return rc;
+        }
+        pitch = Fo;
+        ldG = (int64_t)K * Fo + 2 * G;
+        if ((rc = gnnml3_spmm_k(rowptrT, colT, permT, eaw, gpre, w.ldg, N, K, Fo, Gp, ldG, stream))) return rc;
+        if (G > 0) {
+            k_copy_block<<<cdiv(N * 2 * G, 256) > 1184 ? 1184 : cdiv(N * 2 * G, 256), 256, 0, st>>>(gpre + Fo4, w.ldg, Gp + (int64_t)K * Fo, ldG,
+                                                                                                 N, 2 * G);
+            GNNML3_LAUNCH_CHECK();
+        }
     }
-    // weight gradients: x^T [S_0^T gc .. S_{K-1}^T gc | g1 | g2]
-    float* Gp = (float*)(ws + w.Gp);
-    const int64_t ldG = (int64_t)K * Fo + 2 * G;
-    if ((rc = gnnml3_spmm_k(rowptrT, colT, permT, eaw, gpre, w.ldg, N, K, Fo, Gp, ldG, stream))) return rc;
-    if (G > 0) {
-        k_copy_block<<<cdiv(N * 2 * G, 256) > 1184 ? 1184 : cdiv(N * 2 * G, 256), 256, 0, st>>>(gpre + Fo4, w.ldg, Gp + (int64_t)K * Fo, ldG, N,
-                                                                                             2 * G);
-        GNNML3_LAUNCH_CHECK();
-    }
-    float* dcat = (float*)(ws + w.dcat);
-    if ((rc = gnnml3_gemm_tn(x, ldx, Gp, ldG, dcat, ldG, N, Fi, (int)ldG, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream))) return rc;
-    k_unpack_dw<<<cdiv((int64_t)K * Fi * Fo + 2 * G * Fi, 256), 256, 0, st>>>(dcat, K, Fi, Fo, G, dwconv, dw11, dw12);
+    const int ncols = K * pitch + 2 * G;
+    if ((rc = gnnml3_gemm_tn(x, ldx, Gp, ldG, dcat, ncols, N, Fi, ncols, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream))) return rc;
+    k_unpack_dw<<<cdiv((int64_t)K * Fi * Fo + 2 * G * Fi, 256), 256, 0, st>>>(dcat, K, Fi, Fo, G, pitch, dwconv, dw11, dw12);
     GNNML3_LAUNCH_CHECK();
     // edge-feature gradient: fused dH + SDDMM, then back through the edge MLP
     if (w1 || need_dea) {

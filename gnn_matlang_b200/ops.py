@@ -318,7 +318,7 @@ def fused_supported(K, Kstride, F, Nc, Fs=0, self_mode=0, Ns=0):
 
 
 def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mode=0, Bself=None, bias_s=None, G=0,
-                   epilogue=0):
+                   epilogue=0, hout=None):
     """Fused aggregate + project (gnnml3_fused_agg_proj).  x [*, F] and S [N, Fs] must satisfy ``aligned_rows``.
     epilogue 0 -> out [N, Nc];  epilogue 1 -> (y [N, Nc + G], aux [N, 2G]) = the ML3Layer node branch."""
     lib = _lib.load()
@@ -357,7 +357,8 @@ def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mod
             _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(ea), K, K, _lib.ptr(x), _ld(x), F,
             _lib.ptr(S) if self_mode else None, _ld(S) if self_mode else 0, Fs, self_mode, _lib.ptr(Bmain), _ld(Bmain),
             _lib.ptr(Bself) if self_mode else None, _ld(Bself) if self_mode else 0, Ns, _lib.ptr(bias), _lib.ptr(bias_s),
-            N, Nc, _lib.ptr(out), ldo, _lib.ptr(aux), 2 * G, G, epilogue, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            N, Nc, _lib.ptr(out), ldo, _lib.ptr(aux), 2 * G, G, epilogue, _lib.ptr(hout), _ld(hout) if hout is not None else 0,
+            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
             "gnnml3_fused_agg_proj")
     return out, aux
 

@@ -145,13 +145,19 @@ GNNML3_API int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* au
  *   self_mode 2: main[t, :] += S[t, :] Bself [Fs, Nc]  (SpectConv selfconn; gate gradients in the dx pass).
  * epilogue 0: out [N, Nc] = main.  X and S rows must be 16-byte aligned (ld % 4 == 0) and every column below
  * ceil4(F) / ceil4(Fs) must hold finite values.  3xTF32 arithmetic (FP32-grade).  Backward dx = the same call over the
- * transposed CSR with X = d pre, Bmain = W_k^T.
+ * transposed CSR with X = d pre, Bmain = W_k^T.  hout (nullable, [N, ldh]) receives a copy of the aggregate: support k in
+ * columns [k * Fp, k * Fp + F) with Fp = 32 * ceil(F / 32) (zero padded), the self block S behind them at K * Fp (32 columns) --
+ * the operand of the weight-gradient contraction x^T [S_0^T g .. S_{K-1}^T g | g1 g2], so the backward needs no separate SpMM.
  * --------------------------------------------------------------------------------------------------- */
 /* debugging aid: cycle counters of the fused kernel's warp roles (all zero unless GNNML3_FUSED_DEBUG=1); synchronises */
 GNNML3_API int gnnml3_fused_debug_counters(unsigned long long* out8_host, int reset);
 /* aggregator mode of gnnml3_fused_agg_proj: 0 (default) gathers from global memory with the weight planes resident in shared
  * memory, 1 prefetches every warp's next tile into shared-memory slots with cp.async; returns the previous mode */
 GNNML3_API int gnnml3_fused_set_mode(int slot_mode);
+/* measurement aid (bench.py roofline): CUDA events on the launching stream around every fused launch while enabled;
+ * fetch synchronises and writes [n][10] doubles: ms, N, K, F, Nc, Fs, self_mode, Ns, G, has_perm */
+GNNML3_API int gnnml3_fused_profile(int enable);
+GNNML3_API int gnnml3_fused_profile_fetch(double* out, int max_records);
 GNNML3_API int gnnml3_fused_supported(int K, int Kstride, int F, int Nc, int Fs, int self_mode, int Ns);
 GNNML3_API size_t gnnml3_fused_workspace_bytes(int K, int F, int Nc, int self_mode);
 GNNML3_API int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea,
@@ -159,7 +165,7 @@ GNNML3_API int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
                           int Fs, int self_mode, const float* Bmain, int64_t ldb, const float* Bself,
                           int64_t ldbs, int Ns, const float* bias, const float* bias_s, int64_t N, int Nc,
                           float* out, int64_t ldo, float* aux, int64_t ldaux, int G, int epilogue,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          float* hout, int64_t ldh, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused edge-feature gradient (fused_sddmm.cu):  dea[p, k] = < X[col[p], :], GC[t, :] W[k]^T >  for every CSR slot p of
