@@ -110,12 +110,22 @@ class _SpectConvFn(torch.autograd.Function):
         gout = ops.aligned_rows(gout) if ctx.fused else gout.contiguous()
         fused_dx = (ctx.fused and need_x and (not ctx.selfconn or Fo <= 32)
                     and ops.fused_supported(K, K, Fo, Fi, Fo if ctx.selfconn else 0, 2 if ctx.selfconn else 0, 0))
+        G = None
         if fused_dx:
-            # dx = sum_k S_k^T gout W_k^T (+ gout W_K^T): the same fused kernel over the transposed CSR
+            # dx = sum_k S_k^T gout W_k^T (+ gout W_K^T): the same fused kernel over the transposed CSR; when the weight
+            # gradient is wanted too it leaves the aggregate G' = [S_0^T gout .. | gout] behind (no separate SpMM)
+            Fp = (Fo + 31) // 32 * 32
+            side = need_w and ops.fused_side_output_ok()
+            if side:
+                G = torch.empty(N, (K + (1 if ctx.selfconn else 0)) * Fp, dtype=torch.float32, device=x.device)
             dx, _ = ops.fused_agg_proj(plan.rowptrT, plan.colT, plan.permT, ea_s, gout,
                                        weight[:K].transpose(1, 2).reshape(K * Fo, Fi).contiguous(),
                                        S=gout if ctx.selfconn else None, self_mode=2 if ctx.selfconn else 0,
-                                       Bself=weight[K].t().contiguous() if ctx.selfconn else None, epilogue=0)
+                                       Bself=weight[K].t().contiguous() if ctx.selfconn else None, epilogue=0, hout=G)
+            if side:
+                dcat = ops.gemm_tn(x, G, precision=prec)                                          # [Fi, Kw * Fp]
+                dw = dcat.view(Fi, Kw, Fp)[:, :, :Fo].permute(1, 0, 2).contiguous()
+                need_w = False
         if need_w or (need_x and not fused_dx):
             G = _aggregate(plan, ea_s, gout, Kw, transposed=True)           # G_k = S_k^T gout  [N, Kw*Fo]
             if ctx.selfconn:

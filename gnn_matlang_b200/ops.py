@@ -381,6 +381,11 @@ def ml3_act_bwd_y(y, aux, gy, Fo, G):
     return gpre, csum
 
 
+def fused_side_output_ok():
+    """The aggregate side output (``hout``) of fused_agg_proj exists in the default aggregator mode only."""
+    return _lib.load().gnnml3_fused_set_mode(-1) == 0
+
+
 def fused_sddmm_supported(K, Fi, Fo):
     return bool(_lib.load().gnnml3_fused_sddmm_supported(int(K), int(Fi), int(Fo)))
 
