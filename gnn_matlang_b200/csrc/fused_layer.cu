@@ -28,6 +28,9 @@
 
 // cycle counters of the warp roles (gnnml3_fused_debug_counters): compiled in only with -DFL_PROFILE, they cost issue
 // slots and registers in the single-thread control loops that pace the whole kernel
+#ifndef FL_UD
+#define FL_UD 2          // edges in flight per lane in the global-gather aggregator
+#endif
 #ifdef FL_PROFILE
 #define FL_CNT(...) __VA_ARGS__
 #else
@@ -643,7 +646,7 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                     for (int k = 0; k < KT; ++k)
 #pragma unroll
                         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-                    constexpr int U = 2;   // edges in flight per lane
+                    constexpr int U = FL_UD;   // edges in flight per lane
                     // the CSR slots of the NEXT iteration are fetched one iteration ahead, so that the index -> gather chain
                     // costs one memory latency per iteration instead of two
                     int sidx_n[U], eidx_n[U];
