@@ -105,8 +105,13 @@ static LayerWs layer_ws(int64_t N, int64_t E, int K, int Fi, int Fo, int G) {
     w.ws2 = off; off += a256((size_t)2 * G * Fi * 4 + 4);
     w.Gp = off; off += a256((size_t)N * ((K + 1) * 32) * 4);
     {   // the split count of gemm_tn depends on the column count: size for both layouts of G' (pitch 32 / pitch Fo)
-        const size_t t1 = gnnml3_gemm_tn_workspace_bytes(N, Fi, K * 32 + 2 * G), t2 = gnnml3_gemm_tn_workspace_bytes(N, Fi, K * Fo + 2 * G);
-        w.tn = off; off += a256(t1 > t2 ? t1 : t2);
+        size_t t = gnnml3_gemm_tn_workspace_bytes(N, Fi, K * 32 + 2 * G);
+        const size_t t2 = gnnml3_gemm_tn_workspace_bytes(N, Fi, K * Fo + 2 * G), t3 = gnnml3_gemm_tn_workspace_bytes(N, Fi, K * 32),
+                     t4 = gnnml3_gemm_tn_workspace_bytes(N, Fi, 2 * G > 0 ? 2 * G : 1);
+        t = t > t2 ? t : t2;
+        t = t > t3 ? t : t3;
+        t = t > t4 ? t : t4;
+        w.tn = off; off += a256(t);
     }
     w.dcat = off; off += a256((size_t)Fi * (K * 32 + 2 * G) * 4);
     w.dea2 = off; off += a256((size_t)E * K * 4 + 4);
@@ -203,7 +208,16 @@ extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* co
         }
     }
     const int ncols = K * pitch + 2 * G;
-    if ((rc = gnnml3_gemm_tn(x, ldx, Gp, ldG, dcat, ncols, N, Fi, ncols, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream))) return rc;
+    if (pitch == 32 && G > 0) {
+        // K * 32 columns are exactly four 64-wide column tiles of the contraction kernel; the 2G gate columns would open a
+        // fifth, almost empty one (+30 % time), so they get their own small contraction straight from d pre
+        if ((rc = gnnml3_gemm_tn(x, ldx, Gp, ldG, dcat, ncols, N, Fi, K * 32, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream))) return rc;
+        if ((rc = gnnml3_gemm_tn(x, ldx, gpre + Fo4, w.ldg, dcat + K * 32, ncols, N, Fi, 2 * G, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn,
+                                 stream)))
+            return rc;
+    } else if ((rc = gnnml3_gemm_tn(x, ldx, Gp, ldG, dcat, ncols, N, Fi, ncols, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream))) {
+        return rc;
+    }
     k_unpack_dw<<<cdiv((int64_t)K * Fi * Fo + 2 * G * Fi, 256), 256, 0, st>>>(dcat, K, Fi, Fo, G, pitch, dwconv, dw11, dw12);
     GNNML3_LAUNCH_CHECK();
     // edge-feature gradient: fused dH + SDDMM, then back through the edge MLP
