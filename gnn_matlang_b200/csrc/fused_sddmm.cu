@@ -4,10 +4,14 @@
 // The two-kernel path first materialises dH = grad_out [W_0^T .. W_{K-1}^T]  ([N, K*Fi], a GEMM) in HBM and then runs an
 // SDDMM over the CSR that reads it back.  Here a persistent CTA owns a tile of 64 dst rows:
 //   * the tile's rows of grad_out (conv columns of d pre) are written as raw + residual TF32 planes; one thread issues
-//     tcgen05.mma with the weights on the M side -- plane p holds rows [hi ; lo] of the 64 (k, i) pairs 64p .. 64p+63
-//     of Wr[(k,i), o] = W[k, i, o], resident in shared memory -- and the tile rows on the N side ([hi | lo], N = 128):
-//     16 instructions per tile produce all four 3xTF32 partial products of the whole dH tile in tensor memory;
-//   * epilogue warps add the partial products and transpose dH[(k,i), t] -> dH[t][(k,i)] into shared memory;
+//     tcgen05.mma with the weights on the M side -- accumulator p covers the 128 (k, i) pairs 128p .. 128p+127 of
+//     Wr[(k,i), o] = W[k, i, o]; the hi and lo parts of the weights are CONCATENATED ALONG K (two resident 128-row planes
+//     per accumulator, the grad_out planes are simply read twice), so hi and lo weight products add inside the tensor
+//     core and every accumulator lane is one finished (k, i) row -- and the tile rows on the N side ([hi | lo], N = 128):
+//     16 instructions per tile produce the whole 3xTF32 dH tile in tensor memory (two buffers: the MMAs of the next tile
+//     overlap the drain of this one);
+//   * the four epilogue warps add the hi/lo column halves and transpose dH[(k,i), t] -> dH[t][(k,i)] into shared memory,
+//     each on its own 32 lanes, no exchange between them;
 //   * SDDMM warps (4 lanes per row) keep the row's K x 8 slice of dH in registers, gather each source row once per edge
 //     with 128-bit loads and reduce-scatter the K dot products over the row's lanes (no atomics, fixed order).
 // dH never touches HBM.  Supported: K * 32 <= 256 (K <= 8), Fi <= 32, Fo <= 32 -- every GNNML3 layer of the ZINC
@@ -45,7 +49,8 @@ __device__ __forceinline__ float sd_lo(float v) { return v - __uint_as_float(__f
 template <int K>
 __global__ void __launch_bounds__(SD_THREADS, 1)
 k_fused_sddmm(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ SDParams P) {
-    constexpr int NP = (K * 32 + 63) / 64;           // weight planes / TMEM accumulators (<= 4)
+    constexpr int NACC = (K * 32 + 127) / 128;       // TMEM accumulators of 128 (k, i) rows each (<= 2)
+    constexpr int NP = 2 * NACC;                     // weight planes: hi and lo of every accumulator's rows
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* wres = smem;                                             // [4][SD_WPLANE]
@@ -55,20 +60,20 @@ k_fused_sddmm(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ 
     uint64_t* wfull = bars;          // weights landed
     uint64_t* gfull = bars + 1;      // grad_out planes written        (SD_NW arrivals)   -> MMA
     uint64_t* gempty = bars + 2;     // ... consumed                   (MMA commit)       -> SDDMM warps
-    uint64_t* tfull = bars + 3;      // dH tile complete in TMEM       (MMA commit)       -> epilogue
-    uint64_t* tempty = bars + 4;     // TMEM drained                   (4 arrivals)       -> MMA
-    uint64_t* hfull = bars + 5;      // [2] dH tile in shared memory   (4 arrivals)       -> SDDMM warps
-    uint64_t* hempty = bars + 7;     // [2] ... consumed               (SD_NW arrivals)   -> epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* tfull = bars + 3;      // [2] dH tile complete in TMEM   (MMA commit)       -> epilogue
+    uint64_t* tempty = bars + 5;     // [2] TMEM buffer drained        (4 arrivals)       -> MMA
+    uint64_t* hfull = bars + 7;      // [2] dH tile in shared memory   (4 arrivals)       -> SDDMM warps
+    uint64_t* hempty = bars + 9;     // [2] ... consumed               (SD_NW arrivals)   -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(wfull, 1);
         mbar_init(gfull, SD_NW);
         mbar_init(gempty, 1);
-        mbar_init(tfull, 1);
-        mbar_init(tempty, 4);
         for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull + b, 1);
+            mbar_init(tempty + b, 4);
             mbar_init(hfull + b, 4);
             mbar_init(hempty + b, SD_NW);
         }
@@ -93,62 +98,55 @@ k_fused_sddmm(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ 
             mbar_wait(wfull, 0);
             uint32_t tt = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
+                const uint32_t tb = tt & 1;
                 mbar_wait(gfull, tt & 1);
-                mbar_wait(tempty, (tt & 1) ^ 1);
+                mbar_wait(tempty + tb, ((tt >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint64_t dg = make_kmajor_sw128_desc(smem_u32(gpl));               // N side: [gc raw ; gc lo] rows
 #pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const uint64_t dw = make_kmajor_sw128_desc(smem_u32(wres + (size_t)p * SD_WPLANE));
+                for (int p = 0; p < NACC; ++p) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                        umma_tf32(tmem_base + p * 128, dw + adv, dg + adv, idesc, k == 0 ? 0u : 1u);
+                    for (int h = 0; h < 2; ++h) {                                          // weight hi plane, then lo plane
+                        const uint64_t dw = make_kmajor_sw128_desc(smem_u32(wres + (size_t)(2 * p + h) * SD_WPLANE));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            umma_tf32(tmem_base + tb * 256 + p * 128, dw + adv, dg + adv, idesc, (h == 0 && k == 0) ? 0u : 1u);
+                        }
                     }
                 }
                 umma_commit(gempty);
-                umma_commit(tfull);
+                umma_commit(tfull + tb);
             }
         }
     } else if (warp < 4) {
         // =================================================================== epilogue: TMEM -> dH[t][(k,i)] in shared memory
-        // accumulator p: lane m = plane row (0-63: hi rows of (k,i) = 64p + m; 64-127: lo rows), column n = tile row
-        // (n < 64: x gc_hi, n >= 64: x gc_lo).  Warps 0,1 store hi-row sums, then warps 2,3 add the lo-row sums.
+        // accumulator p: lane m = (k,i) row 128p + m, column n = tile row (n < 64: x gc_hi, n >= 64: x gc_lo)
         const int q = warp;
         uint32_t tt = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
             const uint32_t hb = tt & 1;
-            mbar_wait(tfull, tt & 1);
+            mbar_wait(tfull + hb, (tt >> 1) & 1);
             mbar_wait(hempty + hb, ((tt >> 1) & 1) ^ 1);
             tc_fence_after();
             float* dh = dhs + (size_t)hb * SD_ROWS * SD_LD;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + hb * 256;
 #pragma unroll 1
-            for (int phase = 0; phase < 2; ++phase) {
-                if ((q >> 1) == phase) {
+            for (int p = 0; p < NACC; ++p) {
+                float* dcol = dh + 128 * p + 32 * q + lane;
 #pragma unroll 1
-                    for (int p = 0; p < NP; ++p) {
-                        float* dcol = dh + 64 * p + 32 * (q & 1) + lane;
-#pragma unroll 1
-                        for (int t0 = 0; t0 < SD_ROWS; t0 += 16) {
-                            float vh[16], vl[16];
-                            tmem_ld16(taddr + p * 128 + t0, vh);
-                            tmem_ld16(taddr + p * 128 + SD_ROWS + t0, vl);
+                for (int t0 = 0; t0 < SD_ROWS; t0 += 16) {
+                    float vh[16], vl[16];
+                    tmem_ld16(taddr + p * 128 + t0, vh);
+                    tmem_ld16(taddr + p * 128 + SD_ROWS + t0, vl);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                float v = vh[i] + vl[i];
-                                if (phase == 1) v += dcol[(t0 + i) * SD_LD];
-                                dcol[(t0 + i) * SD_LD] = v;
-                            }
-                        }
-                    }
+                    for (int i = 0; i < 16; ++i) dcol[(t0 + i) * SD_LD] = vh[i] + vl[i];
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(tempty);
+                mbar_arrive(tempty + hb);
                 mbar_arrive(hfull + hb);
             }
         }
@@ -289,17 +287,18 @@ k_fused_sddmm(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ 
     if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
-// Weight planes: plane p, row r < 64: hi of Wr[(k, i) = 64p + r][o] = W[k, i, o] (i < Fi, o < Fo, zero padded), rows 64..127 lo
+// Weight planes: plane 2a + h (a = accumulator, h = 0 hi / 1 lo), row r: Wr[(k, i) = 128a + r][o] = W[k, i, o]
+// (i < Fi, o < Fo, zero padded; hi = RN-TF32, lo = residual)
 __global__ void k_sd_prep_weights(const float* __restrict__ W, int K, int Fi, int Fo, float* __restrict__ planes) {
-    const int np = (K * 32 + 63) / 64;
-    const int total = np * 128 * 32;
+    const int nacc = (K * 32 + 127) / 128;
+    const int total = 2 * nacc * 128 * 32;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int p = idx / (128 * 32), m = (idx / 32) % 128, o = idx % 32;
-        const int ki = 64 * p + (m % 64), k = ki / 32, i = ki % 32;
+        const int pl = idx / (128 * 32), r = (idx / 32) % 128, o = idx % 32;
+        const int ki = 128 * (pl >> 1) + r, k = ki / 32, i = ki % 32;
         float v = 0.f;
         if (k < K && i < Fi && o < Fo) v = __ldg(W + ((int64_t)k * Fi + i) * Fo + o);
         const float h = tf32_rn(v);
-        planes[idx] = m >= 64 ? v - h : h;
+        planes[idx] = (pl & 1) ? v - h : h;
     }
 }
 
@@ -340,7 +339,7 @@ extern "C" int gnnml3_fused_sddmm(const int32_t* rowptr, const int32_t* col, con
     float* planes = (float*)workspace;
     k_sd_prep_weights<<<64, 256, 0, st>>>(W, K, Fi, Fo, planes);
     GNNML3_LAUNCH_CHECK();
-    const int np = (K * 32 + 63) / 64;
+    const int np = 2 * ((K * 32 + 127) / 128);
     CUtensorMap mW;
     int rc;
     if ((rc = make_map(&mW, planes, (int64_t)np * 128, 32, 32, 128))) return rc;
