@@ -298,6 +298,8 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 atomicAdd(P.dbg + 4, (unsigned long long)c_tempty);
                 atomicAdd(P.dbg + 5, (unsigned long long)(clock64() - c_begin));
                 atomicAdd(P.dbg + 10, (unsigned long long)c_issue);
+                atomicMax(P.dbg + 11, (unsigned long long)(clock64() - c_begin));
+                atomicMin(P.dbg + 12, (unsigned long long)(clock64() - c_begin));
             })
         }
     } else if (warp < 4) {
@@ -832,7 +834,10 @@ extern "C" int gnnml3_fused_debug_counters(unsigned long long* out8_host, int re
     }
     GNNML3_CUDA(cudaDeviceSynchronize());
     GNNML3_CUDA(cudaMemcpy(out8_host, g_fl_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    if (reset) GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 16 * sizeof(unsigned long long)));
+    if (reset) {
+        GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 16 * sizeof(unsigned long long)));
+        GNNML3_CUDA(cudaMemset(g_fl_dbg + 12, 0xff, sizeof(unsigned long long)));      // slot 12 is a minimum
+    }
     return GNNML3_OK;
 }
 

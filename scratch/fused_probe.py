@@ -42,6 +42,7 @@ def timeit(fn, name):
         nagg = c[2] and round(c[2] / (c[5] or 1))
         print("   per launch (cycles summed over CTAs): agg gather %.3g wait %.3g total %.3g | mma wait_full %.3g wait_tempty %.3g total %.3g | epi wait %.3g total %.3g"
               % tuple(c[:8]))
+        print("   MMA-thread loop cycles per CTA: mean %.3g  max %.3g  min %.3g (last launch)" % (c[5] / 148, buf[11], buf[12]))
         print("   mma issue+commit cycles per CTA %.3g (of total %.3g)" % (c[10] / 148, c[5] / 148))
         print("   fractions: agg gather %.2f wait %.2f | mma wait_full %.2f wait_tempty %.2f busy %.2f | epi wait %.2f"
               % (c[0] / c[2], c[1] / c[2], c[3] / c[5], c[4] / c[5], 1 - (c[3] + c[4]) / c[5], c[6] / c[7]))
