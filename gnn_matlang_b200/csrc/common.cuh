@@ -42,6 +42,17 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncSetAttribute is per device: `flags` is a per-kernel static array, true once the attribute was set on the current
+// device (a process normally drives one GPU, but nothing here assumes it).  Benign race: the attribute call is idempotent.
+static inline bool first_use_on_device(bool (&flags)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 

@@ -390,11 +390,10 @@ static int launch_edge_bwd(const float* ea, const int32_t* eperm, const float* g
                            const float* w3, const float* w4, int64_t E, float* dea, float* dw1, float* dw2, float* dw3,
                            float* dw4, float* partial, cudaStream_t st) {
     using C = EMC<K>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_edge_mlp_bwd<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem));
         GNNML3_CUDA(cudaFuncSetAttribute(k_edge_mlp_bwd<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem));
-        configured = true;
     }
     const int nb = bwd_blocks(E);
     if (dea)

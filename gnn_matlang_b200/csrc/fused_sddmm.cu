@@ -314,10 +314,9 @@ extern "C" size_t gnnml3_fused_sddmm_workspace_bytes(int K) { return align_up((s
 
 template <int K>
 static int sd_launch(const CUtensorMap& mW, SDParams& P, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_fused_sddmm<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM));
-        configured = true;
     }
     const int grid = P.n_tiles < kNumSMs ? P.n_tiles : kNumSMs;
     k_fused_sddmm<K><<<grid, SD_THREADS, SD_SMEM, st>>>(mW, P);

@@ -408,11 +408,10 @@ using namespace gnnml3;
 template <int BN, bool VA, bool VB, bool X3>
 static int launch_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                      int64_t M, int Nc, int Kc, int epi, cudaStream_t st) {
-    static bool configured = false;  // benign race: the attribute call is idempotent
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_nn<BN, VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)nn_smem_bytes<BN>()));
-        configured = true;
     }
     dim3 grid(cdiv(M, NN_BM), cdiv(Nc, BN));
     k_gemm_nn<BN, VA, VB, X3><<<grid, NN_THREADS, nn_smem_bytes<BN>(), st>>>(A, lda, B, ldb, bias, C, ldc, M, Nc, Kc, epi);
@@ -460,10 +459,9 @@ extern "C" size_t gnnml3_gemm_tn_workspace_bytes(int64_t M, int Ka, int Nb) {
 template <int BA, bool VA, bool VB, bool X3>
 static int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb,
                      int splits, int64_t rps, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn<BA, VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem_bytes<BA>()));
-        configured = true;
     }
     dim3 grid(cdiv(Ka, BA), cdiv(Nb, TN_BB), splits);
     k_gemm_tn<BA, VA, VB, X3><<<grid, TN_THREADS, tn_smem_bytes<BA>(), st>>>(A, lda, B, ldb, P, M, Ka, Nb, rps);
