@@ -363,10 +363,22 @@ def main():
         barrier()
         t0 = time.perf_counter()
         e0.record()
+        # every step's loss is read back to the host: the device -> host copy is enqueued right behind the step (pinned
+        # buffer, non-blocking) and harvested while the next step is being enqueued, so the read never stalls the pipeline
+        loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        lv = float("nan")
         for i in range(args.steps):
             b = feeder.get()
             feeder.prefetch(host_ring[(i + 4) % args.ring])
-            lv = float(trainer.step(b).item())           # device -> host read of the step's loss
+            lt = trainer.step(b)
+            loss_host[i & 1].copy_(lt.reshape(1), non_blocking=True)      # device -> host read of the step's loss
+            loss_ev[i & 1].record()
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                lv = float(loss_host[(i - 1) & 1][0])
+        loss_ev[(args.steps - 1) & 1].synchronize()
+        lv = float(loss_host[(args.steps - 1) & 1][0])
         e1.record()
         barrier()
         ms2 = e0.elapsed_time(e1)
