@@ -386,8 +386,19 @@ def main():
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         ms2 = float(t2.item())
+        # this box's pinned host -> device rate for one batch (explains e2e when the link, not the GPU, is the bound:
+        # a step needs h2d_bytes_per_step / ms_per_step of it)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(3):
+            host_ring[i % args.ring].to(dev, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * batch_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
         e2e = {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": int(batch_bytes),
-               "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps, "last_loss": lv}
+               "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps, "last_loss": lv,
+               "h2d_link_gbs_measured": round(h2d_gbs, 2)}
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): oracle port, bounded sample
     cpu = None

@@ -27,9 +27,9 @@ struct EMC {
     static constexpr int NT1 = (KP / 4) * (T / 4);    // 4x4 tiles of M1 = d_pre4^T tmp      [KP x T]
     static constexpr int NT2 = (DP / 4) * (KP / 4);   // 4x4 tiles of M2 = d_pre123^T in     [DP x KP]
     static constexpr int NT = NT1 + NT2;
-    static constexpr int THREADS = 256;
+    static constexpr int THREADS = 256;   // backward block: 320 / 384 threads (fewer registers, more warps) spill and measured 11 % slower
     static constexpr int GROUPS = (THREADS / NT) < 1 ? 1 : (THREADS / NT);
-    static constexpr int TILE_E = 256;
+    static constexpr int TILE_E = THREADS;
     static constexpr int W123 = 3 * H * KP;           // smem floats for W1..W3 (rows padded to KP)
     static constexpr int W4 = K * T;
     static constexpr int NOUT = K * T + 3 * H * K;    // number of weight-gradient entries
@@ -130,7 +130,7 @@ k_edge_mlp_fwd(const float* __restrict__ ea, const int* __restrict__ eperm, cons
 // and stage [d_pre4 | tmp | d_pre123 | in] in shared memory.  Phase 2 (thread = 4x4 tile of the weight-gradient
 // matrices, GROUPS thread groups splitting the tile's edges): accumulate the outer products.
 template <int K, bool DIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(EMC<K>::THREADS)
 k_edge_mlp_bwd(const float* __restrict__ ea, const int* __restrict__ eperm, const float* __restrict__ gout,
                const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
                const float* __restrict__ w4, int64_t E, float* __restrict__ dea, float* __restrict__ partial) {
@@ -314,34 +314,48 @@ k_edge_mlp_bwd(const float* __restrict__ ea, const int* __restrict__ eperm, cons
     }
 }
 
+// 32 outputs per block, 8 split-lanes per output summing every 8th block partial (independent loads), then a fixed tree.
 template <int K>
-__global__ void k_edge_mlp_bwd_reduce(const float* __restrict__ partial, int nblocks, float* __restrict__ dw1,
-                                      float* __restrict__ dw2, float* __restrict__ dw3, float* __restrict__ dw4) {
+__global__ void __launch_bounds__(256)
+k_edge_mlp_bwd_reduce(const float* __restrict__ partial, int nblocks, float* __restrict__ dw1, float* __restrict__ dw2,
+                      float* __restrict__ dw3, float* __restrict__ dw4) {
     using C = EMC<K>;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C::NOUT) return;
-    int r, c, idx;
-    float* dst;
-    if (i < K * C::T) {               // dW4[k][j] = M1[k][j]
-        r = i / C::T;
-        c = i % C::T;
-        idx = ((r / 4) * (C::T / 4) + c / 4) * 16 + (r % 4) * 4 + (c % 4);
-        dst = dw4 + i;
-    } else {                          // dW{1,2,3}[j][i] = M2[m*2K + j][i]
-        const int q = i - K * C::T;
-        const int m = q / (C::H * K), jj = (q / K) % C::H;
-        c = q % K;
-        r = m * C::H + jj;
-        idx = (C::NT1 + (r / 4) * (C::KP / 4) + c / 4) * 16 + (r % 4) * 4 + (c % 4);
-        dst = (m == 0 ? dw1 : (m == 1 ? dw2 : dw3)) + jj * K + c;
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    int idx = 0;
+    float* dst = nullptr;
+    if (i < C::NOUT) {
+        int r, c;
+        if (i < K * C::T) {               // dW4[k][j] = M1[k][j]
+            r = i / C::T;
+            c = i % C::T;
+            idx = ((r / 4) * (C::T / 4) + c / 4) * 16 + (r % 4) * 4 + (c % 4);
+            dst = dw4 + i;
+        } else {                          // dW{1,2,3}[j][i] = M2[m*2K + j][i]
+            const int q = i - K * C::T;
+            const int m = q / (C::H * K), jj = (q / K) % C::H;
+            c = q % K;
+            r = m * C::H + jj;
+            idx = (C::NT1 + (r / 4) * (C::KP / 4) + c / 4) * 16 + (r % 4) * 4 + (c % 4);
+            dst = (m == 0 ? dw1 : (m == 1 ? dw2 : dw3)) + jj * K + c;
+        }
     }
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * C::NT * 16 + idx];
-    *dst = s;
+    if (dst)
+        for (int b = ty; b < nblocks; b += 8) s += __ldg(partial + (size_t)b * C::NT * 16 + idx);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && dst) {
+        float v = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) v += red[y][tx];
+        *dst = v;
+    }
 }
 
-static int bwd_blocks(int64_t E) {
-    int64_t t = (E + 255) / 256;
+static int bwd_blocks(int64_t E, int tile_e) {
+    int64_t t = (E + tile_e - 1) / tile_e;
     int64_t cap = kNumSMs;  // one resident block per SM (the staging tile is 50-200 KB)
     return (int)(t < 1 ? 1 : (t > cap ? cap : t));
 }
@@ -382,7 +396,7 @@ extern "C" int gnnml3_edge_mlp_fwd(const float* ea, const int32_t* eperm, const 
 extern "C" size_t gnnml3_edge_mlp_bwd_workspace_bytes(int64_t E, int K) {
     const int KP = pad4(K), T = 4 * K, DP = pad4(6 * K);
     const size_t nt = (size_t)(KP / 4) * (T / 4) + (size_t)(DP / 4) * (KP / 4);
-    return align_up((size_t)bwd_blocks(E) * nt * 16 * sizeof(float), 256);
+    return align_up((size_t)bwd_blocks(E, 256) * nt * 16 * sizeof(float), 256);   // 256 = smallest tile = most blocks
 }
 
 template <int K>
@@ -395,13 +409,13 @@ static int launch_edge_bwd(const float* ea, const int32_t* eperm, const float* g
         GNNML3_CUDA(cudaFuncSetAttribute(k_edge_mlp_bwd<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem));
         GNNML3_CUDA(cudaFuncSetAttribute(k_edge_mlp_bwd<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem));
     }
-    const int nb = bwd_blocks(E);
+    const int nb = bwd_blocks(E, C::TILE_E);
     if (dea)
-        k_edge_mlp_bwd<K, true><<<nb, 256, C::bwd_smem, st>>>(ea, eperm, gout, w1, w2, w3, w4, E, dea, partial);
+        k_edge_mlp_bwd<K, true><<<nb, C::THREADS, C::bwd_smem, st>>>(ea, eperm, gout, w1, w2, w3, w4, E, dea, partial);
     else
-        k_edge_mlp_bwd<K, false><<<nb, 256, C::bwd_smem, st>>>(ea, eperm, gout, w1, w2, w3, w4, E, dea, partial);
+        k_edge_mlp_bwd<K, false><<<nb, C::THREADS, C::bwd_smem, st>>>(ea, eperm, gout, w1, w2, w3, w4, E, dea, partial);
     GNNML3_LAUNCH_CHECK();
-    k_edge_mlp_bwd_reduce<K><<<cdiv(C::NOUT, 128), 128, 0, st>>>(partial, nb, dw1, dw2, dw3, dw4);
+    k_edge_mlp_bwd_reduce<K><<<cdiv(C::NOUT, 32), 256, 0, st>>>(partial, nb, dw1, dw2, dw3, dw4);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }

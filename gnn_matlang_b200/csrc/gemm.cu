@@ -223,17 +223,18 @@ k_gemm_nn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 }
 
 // ------------------------------------------------------------------------------------------------ gemm_tn
-constexpr int TN_BB = 64, TN_BK = 32, TN_STAGES = 3, TN_THREADS = 128, TN_LD = 72;
-template <int BA>
-constexpr size_t tn_smem_bytes() { return sizeof(float) * TN_STAGES * TN_BK * (BA + 8 + TN_LD); }
+constexpr int TN_BK = 32, TN_STAGES = 3, TN_THREADS = 128;
+template <int BA, int BB>
+constexpr size_t tn_smem_bytes() { return sizeof(float) * TN_STAGES * TN_BK * (BA + 8 + BB + 8); }
 
 // BA = 64: 2 x 2 warps of 32 x 32;  BA = 32 (Ka <= 32, e.g. x^T G' with 32 input features): 1 x 4 warps of 32 x 16, so
-// no MMA is spent on padding rows of the A^T tile.
-template <int BA, bool VA, bool VB, bool X3>
+// no MMA is spent on padding rows of the A^T tile.  BB = 128 with BA = 32 gives every warp a 32 x 32 tile (the A^T fragments
+// and their hi/lo split are shared by twice as many MMAs); used when B has at least 128 columns.
+template <int BA, int BB, bool VA, bool VB, bool X3>
 __global__ void __launch_bounds__(TN_THREADS)
 k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ P,
           int64_t M, int Ka, int Nb, int64_t rows_per_split) {
-    constexpr int LDA = BA + 8;
+    constexpr int LDA = BA + 8, TN_BB = BB, TN_LD = BB + 8;
     constexpr int WA = BA / 32, WB = 4 / WA;       // warp grid
     constexpr int NTB = TN_BB / WB / 8;            // n-tiles per warp
     extern __shared__ __align__(16) float smem[];
@@ -272,13 +273,18 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
         cp_async_commit();
         const float* as = As + (kt % TN_STAGES) * TN_BK * LDA + wa * 32;
         const float* bs = Bs + (kt % TN_STAGES) * TN_BK * TN_LD + wb * (TN_BB / WB);
-        float tacc[2][NTB][4];   // per-k-tile accumulators, see k_gemm_nn
+        // per-k-tile accumulators (see k_gemm_nn); the hi*hi products and the two correction products go to separate
+        // accumulators so a tile's three MMAs do not form one dependent chain (4 -> 8 independent chains per warp)
+        float tacc[2][NTB][4], tlo[X3 ? 2 : 1][X3 ? NTB : 1][4];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < NTB; ++j)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) tacc[i][j][r] = 0.f;
+                for (int r = 0; r < 4; ++r) {
+                    tacc[i][j][r] = 0.f;
+                    if constexpr (X3) tlo[i][j][r] = 0.f;
+                }
 #pragma unroll
         for (int kk = 0; kk < TN_BK / 8; ++kk) {
             float af[2][4];
@@ -309,9 +315,9 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                     split_tf32<2>(bf, bh, bl);
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        mma_tf32(tacc[i][j], al[i], bh);
-                        mma_tf32(tacc[i][j], ah[i], bl);
+                        mma_tf32(tlo[i][j], al[i], bh);
                         mma_tf32(tacc[i][j], ah[i], bh);
+                        mma_tf32(tlo[i][j], ah[i], bl);
                     }
                 } else {
                     bh[0] = f2tf32(bf[0]);
@@ -326,7 +332,10 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
 #pragma unroll
             for (int j = 0; j < NTB; ++j)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) acc[i][j][r] += tacc[i][j][r];
+                for (int r = 0; r < 4; ++r) {
+                    if constexpr (X3) acc[i][j][r] += tacc[i][j][r] + tlo[i][j][r];
+                    else acc[i][j][r] += tacc[i][j][r];
+                }
     }
     cp_async_wait<0>();
     float* Pz = P + (int64_t)blockIdx.z * Ka * Nb;
@@ -341,6 +350,63 @@ k_gemm_tn(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                 if (ra < Ka && cb < Nb) Pz[(int64_t)ra * Nb + cb] = acc[i][j][r];
             }
 }
+
+// Narrow weight gradient (Nb <= 8 columns, Ka <= 64: the tanh-gate columns of ML3Layer, x^T [g11 | g12]).  A 64-column
+// tensor-core tile would spend 16x the MMAs on padding; this is a plain FP32 FMA kernel that streams A once: a warp owns
+// TNN_ROWS_PER_WARP consecutive rows, lane = A column, the Nb values of the B row are warp-uniform loads.  Partials per CTA
+// (8 warps combined in a fixed order) go to the workspace and k_reduce_partials finishes -- deterministic, no atomics.
+constexpr int TNN_MAXNB = 8, TNN_ROWS_PER_WARP = 32, TNN_WARPS = 8, TNN_ROWS = TNN_ROWS_PER_WARP * TNN_WARPS;
+__global__ void __launch_bounds__(TNN_WARPS * 32)
+k_gemm_tn_narrow(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ P,
+                 int64_t M, int Ka, int Nb) {
+    __shared__ float red[TNN_WARPS][2 * 32 * TNN_MAXNB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r0 = (int64_t)blockIdx.x * TNN_ROWS + warp * TNN_ROWS_PER_WARP;
+    const int64_t r1 = min(M, r0 + TNN_ROWS_PER_WARP);
+    float acc[2][TNN_MAXNB];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int b = 0; b < TNN_MAXNB; ++b) acc[h][b] = 0.f;
+    const bool two = Ka > 32;
+    const bool ok0 = lane < Ka, ok1 = lane + 32 < Ka;
+    // TNN_UNR rows per iteration, every load issued before the first FMA (in-order issue: a load placed after a dependent
+    // FMA would wait a full memory latency per row)
+    constexpr int TNN_UNR = 8;
+    for (int64_t rr = r0; rr < r1; rr += TNN_UNR) {
+        float a0[TNN_UNR], a1[TNN_UNR], bv[TNN_UNR][TNN_MAXNB];
+#pragma unroll
+        for (int u = 0; u < TNN_UNR; ++u) {
+            const int64_t r = rr + u;
+            const bool in = r < r1;
+            a0[u] = (in && ok0) ? __ldg(A + r * lda + lane) : 0.f;
+            a1[u] = (in && two && ok1) ? __ldg(A + r * lda + 32 + lane) : 0.f;
+#pragma unroll
+            for (int b = 0; b < TNN_MAXNB; ++b) bv[u][b] = (in && b < Nb) ? __ldg(B + r * ldb + b) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < TNN_UNR; ++u)
+#pragma unroll
+            for (int b = 0; b < TNN_MAXNB; ++b) {
+                acc[0][b] = fmaf(a0[u], bv[u][b], acc[0][b]);
+                acc[1][b] = fmaf(a1[u], bv[u][b], acc[1][b]);
+            }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int b = 0; b < TNN_MAXNB; ++b) red[warp][(h * 32 + lane) * TNN_MAXNB + b] = acc[h][b];
+    __syncthreads();
+    float* Pz = P + (int64_t)blockIdx.x * Ka * Nb;
+    for (int i = threadIdx.x; i < Ka * Nb; i += blockDim.x) {
+        const int a = i / Nb, b = i % Nb;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < TNN_WARPS; ++w) v += red[w][a * TNN_MAXNB + b];
+        Pz[i] = v;
+    }
+}
+static inline bool tn_narrow(int Ka, int Nb) { return Nb <= TNN_MAXNB && Ka <= 64; }
 
 // C[i] = sum_z P[z][i] in a fixed order: 8 split-lanes per output accumulate strided partial sums, then a fixed tree
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ P, int splits, int64_t n, int cols,
@@ -363,8 +429,10 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
 
 static inline int tn_ba_for(int Ka) { return Ka <= 32 ? 32 : 64; }
 
+static inline int tn_bb_for(int Ka, int Nb) { return (Ka <= 32 && Nb >= 128) ? 128 : 64; }
+
 static void tn_plan(int64_t M, int Ka, int Nb, int* splits, int64_t* rows_per_split) {
-    const int tiles = cdiv(Ka, tn_ba_for(Ka)) * cdiv(Nb, TN_BB);
+    const int tiles = cdiv(Ka, tn_ba_for(Ka)) * cdiv(Nb, tn_bb_for(Ka, Nb));
     int s = (4 * kNumSMs + tiles - 1) / tiles;
     int64_t maxs = (M + 4 * TN_BK - 1) / (4 * TN_BK);
     if (s > maxs) s = (int)maxs;
@@ -453,29 +521,30 @@ extern "C" size_t gnnml3_gemm_tn_workspace_bytes(int64_t M, int Ka, int Nb) {
     int splits;
     int64_t rps;
     tn_plan(M > 0 ? M : 1, Ka, Nb, &splits, &rps);
+    if (tn_narrow(Ka, Nb)) splits = (int)cdiv(M > 0 ? M : 1, (int64_t)TNN_ROWS);
     return align_up((size_t)splits * Ka * Nb * sizeof(float), 256);
 }
 
-template <int BA, bool VA, bool VB, bool X3>
+template <int BA, int BB, bool VA, bool VB, bool X3>
 static int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb,
                      int splits, int64_t rps, cudaStream_t st) {
     static bool configured[64] = {};
     if (first_use_on_device(configured)) {
-        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn<BA, VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem_bytes<BA>()));
+        GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn<BA, BB, VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem_bytes<BA, BB>()));
     }
-    dim3 grid(cdiv(Ka, BA), cdiv(Nb, TN_BB), splits);
-    k_gemm_tn<BA, VA, VB, X3><<<grid, TN_THREADS, tn_smem_bytes<BA>(), st>>>(A, lda, B, ldb, P, M, Ka, Nb, rps);
+    dim3 grid(cdiv(Ka, BA), cdiv(Nb, BB), splits);
+    k_gemm_tn<BA, BB, VA, VB, X3><<<grid, TN_THREADS, tn_smem_bytes<BA, BB>(), st>>>(A, lda, B, ldb, P, M, Ka, Nb, rps);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
 
-template <int BA, bool X3>
+template <int BA, int BB, bool X3>
 static int launch_tn_v(bool va, bool vb, const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka,
                        int Nb, int splits, int64_t rps, cudaStream_t st) {
-    if (va && vb) return launch_tn<BA, true, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
-    if (va) return launch_tn<BA, true, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
-    if (vb) return launch_tn<BA, false, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
-    return launch_tn<BA, false, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (va && vb) return launch_tn<BA, BB, true, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (va) return launch_tn<BA, BB, true, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (vb) return launch_tn<BA, BB, false, true, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    return launch_tn<BA, BB, false, false, X3>(A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
 }
 
 extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
@@ -484,7 +553,7 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
     GNNML3_REQUIRE(A && B && C && workspace, "gemm_tn: NULL pointer");
     GNNML3_REQUIRE(lda >= Ka && ldb >= Nb && ldc >= Nb, "gemm_tn: leading dimensions too small");
     GNNML3_REQUIRE(precision == GNNML3_PREC_3XTF32 || precision == GNNML3_PREC_TF32, "gemm_tn: unknown precision %d", precision);
-    GNNML3_REQUIRE(cdiv(Nb, TN_BB) < 65536, "gemm_tn: grid too large");
+    GNNML3_REQUIRE(cdiv(Nb, 64) < 65536, "gemm_tn: grid too large");
     if (workspace_bytes < gnnml3_gemm_tn_workspace_bytes(M, Ka, Nb))
         return set_err(GNNML3_ERR_WORKSPACE, "gemm_tn: workspace %zu < %zu bytes", workspace_bytes,
                        gnnml3_gemm_tn_workspace_bytes(M, Ka, Nb));
@@ -496,12 +565,26 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
     const bool vb = (ldb % 4 == 0 || M == 1) && (uintptr_t)B % 16 == 0;
     float* P = (float*)workspace;
     int rc;
-    if (tn_ba_for(Ka) == 32)
-        rc = precision == GNNML3_PREC_3XTF32 ? launch_tn_v<32, true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
-                                             : launch_tn_v<32, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    if (tn_narrow(Ka, Nb)) {   // exact FP32 FMAs: at least as accurate as either requested precision
+        const int64_t nblk = cdiv(M, (int64_t)TNN_ROWS);
+        GNNML3_REQUIRE(nblk < (int64_t)1 << 31, "gemm_tn: too many rows");
+        k_gemm_tn_narrow<<<(unsigned)nblk, TNN_WARPS * 32, 0, st>>>(A, lda, B, ldb, P, M, Ka, Nb);
+        GNNML3_LAUNCH_CHECK();
+        const int64_t n = (int64_t)Ka * Nb;
+        k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, (int)nblk, n, Nb, C, ldc);
+        GNNML3_LAUNCH_CHECK();
+        return GNNML3_OK;
+    }
+    const bool x3 = precision == GNNML3_PREC_3XTF32;
+    if (tn_ba_for(Ka) == 32 && tn_bb_for(Ka, Nb) == 128)
+        rc = x3 ? launch_tn_v<32, 128, true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
+                : launch_tn_v<32, 128, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+    else if (tn_ba_for(Ka) == 32)
+        rc = x3 ? launch_tn_v<32, 64, true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
+                : launch_tn_v<32, 64, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
     else
-        rc = precision == GNNML3_PREC_3XTF32 ? launch_tn_v<64, true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
-                                             : launch_tn_v<64, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
+        rc = x3 ? launch_tn_v<64, 64, true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
+                : launch_tn_v<64, 64, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
     if (rc) return rc;
     const int64_t n = (int64_t)Ka * Nb;
     k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, splits, n, Nb, C, ldc);
