@@ -408,6 +408,12 @@ k_gemm_tn_narrow(const float* __restrict__ A, int64_t lda, const float* __restri
 }
 static inline bool tn_narrow(int Ka, int Nb) { return Nb <= TNN_MAXNB && Ka <= 64; }
 
+// tcgen05 path for the big weight gradients (gemm_tn_tc.cu)
+bool gemm_tn_tc_shape_ok(int64_t M, int Ka, int Nb);
+bool gemm_tn_tc_ok(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int Ka, int Nb);
+int gemm_tn_tc_parts(int64_t M);
+int gemm_tn_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb, cudaStream_t st);
+
 // C[i] = sum_z P[z][i] in a fixed order: 8 split-lanes per output accumulate strided partial sums, then a fixed tree
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ P, int splits, int64_t n, int cols,
                                                          float* __restrict__ C, int64_t ldc) {
@@ -522,6 +528,7 @@ extern "C" size_t gnnml3_gemm_tn_workspace_bytes(int64_t M, int Ka, int Nb) {
     int64_t rps;
     tn_plan(M > 0 ? M : 1, Ka, Nb, &splits, &rps);
     if (tn_narrow(Ka, Nb)) splits = (int)cdiv(M > 0 ? M : 1, (int64_t)TNN_ROWS);
+    if (gemm_tn_tc_shape_ok(M, Ka, Nb) && gemm_tn_tc_parts(M) > splits) splits = gemm_tn_tc_parts(M);
     return align_up((size_t)splits * Ka * Nb * sizeof(float), 256);
 }
 
@@ -576,6 +583,14 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
         return GNNML3_OK;
     }
     const bool x3 = precision == GNNML3_PREC_3XTF32;
+    static const bool no_tc = getenv("GNNML3_NO_TN_TC") != nullptr;
+    if (x3 && !no_tc && gemm_tn_tc_ok(A, lda, B, ldb, M, Ka, Nb)) {
+        if ((rc = gemm_tn_tc_launch(A, lda, B, ldb, P, M, Ka, Nb, st))) return rc;
+        const int64_t n = (int64_t)Ka * Nb;
+        k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, gemm_tn_tc_parts(M), n, Nb, C, ldc);
+        GNNML3_LAUNCH_CHECK();
+        return GNNML3_OK;
+    }
     if (tn_ba_for(Ka) == 32 && tn_bb_for(Ka, Nb) == 128)
         rc = x3 ? launch_tn_v<32, 128, true>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st)
                 : launch_tn_v<32, 128, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
