@@ -342,8 +342,18 @@ k_edge_mlp_bwd_reduce(const float* __restrict__ partial, int nblocks, float* __r
         }
     }
     float s = 0.f;
-    if (dst)
-        for (int b = ty; b < nblocks; b += 8) s += __ldg(partial + (size_t)b * C::NT * 16 + idx);
+    if (dst) {
+        float s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four loads in flight, fixed order
+        int b = ty;
+        for (; b + 24 < nblocks; b += 32) {
+            s += __ldg(partial + (size_t)b * C::NT * 16 + idx);
+            s1 += __ldg(partial + (size_t)(b + 8) * C::NT * 16 + idx);
+            s2 += __ldg(partial + (size_t)(b + 16) * C::NT * 16 + idx);
+            s3 += __ldg(partial + (size_t)(b + 24) * C::NT * 16 + idx);
+        }
+        for (; b < nblocks; b += 8) s += __ldg(partial + (size_t)b * C::NT * 16 + idx);
+        s = (s + s1) + (s2 + s3);
+    }
     red[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && dst) {

@@ -11,15 +11,16 @@
 //     D1 = [x_hi; x_lo]^T G_hi   (rows 0-31: hi*hi, rows 32-63: lo*hi)      D2 = [x_hi; x_lo]^T G_lo  (rows 0-31: hi*lo)
 //     C  = D1[0:32] + D1[32:64] + D2[0:32]
 // (the tensor core truncates the raw FP32 bits to TF32 = "hi"; lo = v - trunc(v) is exact in FP32).  One persistent CTA per
-// SM owns a contiguous row range; 8 producer warps stream 32-row stages global -> (hi, lo) planes in shared
-// memory (cp.async into the raw/hi planes three stages ahead; the lo planes are computed from them), one thread issues the MMAs, two
+// SM owns a contiguous row range; one thread streams 32-row stages with TMA (SWIZZLE_128B_ATOM_32B boxes = the raw/hi
+// planes, three stages ahead), 8 warps compute the lo planes from them, one thread issues the MMAs, two
 // alternating accumulator sets keep every TMEM accumulation chain at <= M / (148 * 16) adds.  Per-CTA partials go to the
 // workspace and k_reduce_partials (gemm.cu) adds them in a fixed order -- deterministic, no atomics.
 #include "tc_common.cuh"
 
 namespace gnnml3 {
 
-constexpr int TT_ROWS = 32, TT_HI = 3, TT_LO = 3, TT_PRODUCERS = 256, TT_THREADS = TT_PRODUCERS + 32;   // raw / lo slots (4 + 2 measured 4 % slower)
+constexpr int TT_ROWS = 32, TT_HI = 3, TT_LO = 3;             // raw / lo slots
+constexpr int TT_PRODUCERS = 256, TT_THREADS = TT_PRODUCERS + 64;   // 8 split warps + MMA warp + TMA warp
 constexpr int TT_PLANE = TT_ROWS * 128;                       // one 32-column atom column of a stage: 4 KB
 constexpr int TT_NPL = 8;                                     // B planes per stage (Nb <= 256)
 constexpr int TT_HALF = (1 + TT_NPL) * TT_PLANE;              // x plane + 8 G planes of one precision half: 36 KB
@@ -40,17 +41,12 @@ __device__ __forceinline__ uint32_t tt_off(int k, int m) {
     return (uint32_t)((m >> 5) * TT_PLANE + (k >> 2) * 512 + (k & 3) * 128 + (((((m & 31) >> 3) ^ (k & 3))) << 5) + (m & 7) * 4);
 }
 __device__ __forceinline__ float tt_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-// 16-byte cp.async, the bytes past src_bytes zero-filled
-__device__ __forceinline__ void tt_cp16(void* smem_dst, const void* gmem, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem), "r"(src_bytes) : "memory");
-}
-
 __global__ void __launch_bounds__(TT_THREADS, 1)
-k_gemm_tn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ P,
+k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ P,
              int64_t M, int Ka, int Nb, int64_t rows_per_cta) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full[TT_HI], mdone[TT_HI], done;
+    __shared__ uint64_t raw[TT_HI], full[TT_HI], mdone[TT_HI], done;
     __shared__ uint32_t tslot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
     const int64_t rbeg = (int64_t)blockIdx.x * rows_per_cta;
@@ -60,7 +56,7 @@ k_gemm_tn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
     const int nch = Npad >> 2;                                 // 16-byte chunks per B row
 
     if (t == 0) {
-        for (int s = 0; s < TT_HI; ++s) { mbar_init(&full[s], TT_PRODUCERS / 32); mbar_init(&mdone[s], 1); }
+        for (int s = 0; s < TT_HI; ++s) { mbar_init(&raw[s], 1); mbar_init(&full[s], TT_PRODUCERS / 32); mbar_init(&mdone[s], 1); }
         mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -73,46 +69,22 @@ k_gemm_tn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
     uint8_t* hi_ring = smem;                                   // TT_HI x [x_hi | G_hi x 8]
     uint8_t* lo_ring = smem + (size_t)TT_HI * TT_HALF;         // TT_LO x [x_lo | G_lo x 8]
     if (warp < TT_PRODUCERS / 32) {
-        // ------------------------------------------------------------------ producers
-        // raw FP32 rows go global -> hi planes with cp.async (two stages in flight, no registers held); the thread that
-        // copied a 16-byte chunk later reads it back, writes lo = v - trunc(v) to the lo plane and publishes the stage.
+        // ------------------------------------------------------------------ split warps: lo = v - trunc(v), same offsets
         const int xk = t >> 3, xc = (t & 7) * 4;
         const uint32_t xoff = tt_off(xk, xc);
-        int gk[8], gc[8];
+        bool gon[8];
         uint32_t goff[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = t + TT_PRODUCERS * u;
-            gk[u] = i / nch;
-            gc[u] = (i - gk[u] * nch) * 4;
-            goff[u] = TT_PLANE + tt_off(gk[u] & (TT_ROWS - 1), gc[u]);
-        }
-        auto issue = [&](int it) {
-            const int64_t r0 = rbeg + (int64_t)it * TT_ROWS;
-            uint8_t* st = hi_ring + (size_t)(it % TT_HI) * TT_HALF;
-            {
-                int nb = (r0 + xk < rend) ? (Ka - xc) * 4 : 0;
-                nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-                tt_cp16(st + xoff, nb > 0 ? A + (r0 + xk) * lda + xc : A, nb);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (gk[u] < TT_ROWS) {
-                    int nb = (r0 + gk[u] < rend) ? (Nb - gc[u]) * 4 : 0;
-                    nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-                    tt_cp16(st + goff[u], nb > 0 ? B + (r0 + gk[u]) * ldb + gc[u] : B, nb);
-                }
-            }
-        };
-        for (int p = 0; p < TT_HI - 1; ++p) {
-            if (p < nst) issue(p);
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            const int k = i / nch, c = (i - k * nch) * 4;
+            gon[u] = k < TT_ROWS;
+            goff[u] = TT_PLANE + tt_off(k & (TT_ROWS - 1), c);
         }
         for (int it = 0; it < nst; ++it) {
             const int s = it % TT_HI;
-            if constexpr (TT_HI == 3) asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's chunks of stage it landed
-            else asm volatile("cp.async.wait_group 2;" ::: "memory");
-            if (it >= TT_LO) mbar_wait(&mdone[(it - TT_LO) % TT_HI], ((it - TT_LO) / TT_HI) & 1);   // lo slot it % 2 is free again
+            mbar_wait(&raw[s], (it / TT_HI) & 1);                                                    // TMA boxes of stage it landed
+            if (it >= TT_LO) mbar_wait(&mdone[(it - TT_LO) % TT_HI], ((it - TT_LO) / TT_HI) & 1);   // lo slot is free again
             const uint8_t* hs = hi_ring + (size_t)s * TT_HALF;
             uint8_t* ls = lo_ring + (size_t)(it % TT_LO) * TT_HALF;
             {
@@ -121,7 +93,7 @@ k_gemm_tn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                if (gk[u] < TT_ROWS) {
+                if (gon[u]) {
                     const float4 v = *reinterpret_cast<const float4*>(hs + goff[u]);
                     *reinterpret_cast<float4*>(ls + goff[u]) = make_float4(tt_lo(v.x), tt_lo(v.y), tt_lo(v.z), tt_lo(v.w));
                 }
@@ -129,16 +101,24 @@ k_gemm_tn_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);             // one arrival per warp (arrivals on one barrier serialise)
-            // refill the raw slot stage it - 1 used (its MMAs were issued before this stage was split)
-            if (it + TT_HI - 1 < nst) {
-                if (it >= 1) mbar_wait(&mdone[(it - 1) % TT_HI], ((it - 1) / TT_HI) & 1);
-                issue(it + TT_HI - 1);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (warp == TT_PRODUCERS / 32 + 1) {
+        // ------------------------------------------------------------------ TMA issuer: x box + Npad / 32 G boxes per stage
+        if (lane == 0) {
+            const int npl = Npad >> 5;
+            const uint32_t bytes = (uint32_t)(1 + npl) * TT_PLANE;
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % TT_HI;
+                if (it >= TT_HI) mbar_wait(&mdone[s], ((it / TT_HI) - 1) & 1);      // MMAs that read this raw slot are done
+                uint8_t* st = hi_ring + (size_t)s * TT_HALF;
+                const int r0 = (int)(rbeg + (int64_t)it * TT_ROWS);
+                mbar_arrive_expect_tx(&raw[s], bytes);
+                tma_load_2d(st, &mapA, &raw[s], 0, r0);
+                for (int pl = 0; pl < npl; ++pl) tma_load_2d(st + (size_t)(1 + pl) * TT_PLANE, &mapB, &raw[s], 32 * pl, r0);
+            }
+        }
     } else if (lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------------ MMA issuer (warp 8)
         const uint32_t idesc = make_idesc_tf32_mn(64, Npad, true, true);
         for (int it = 0; it < nst; ++it) {
             const int s = it % TT_HI;
@@ -210,16 +190,35 @@ int gemm_tn_tc_parts(int64_t M) {
 bool gemm_tn_tc_ok(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int Ka, int Nb) {
     return gemm_tn_tc_shape_ok(M, Ka, Nb) && lda % 4 == 0 && ldb % 4 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0;
 }
+// row-major FP32 [rows, cols] (row stride ld) -> boxes of 32 columns x TT_ROWS rows in the 128B-swizzle / 32B-atom pattern
+// (= UMMA SWIZZLE_128B_BASE32B); columns / rows outside the matrix are zero-filled by the TMA unit
+static int tt_make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+    PFN_encodeTiled enc = get_encoder();
+    if (!enc) return set_err(GNNML3_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)TT_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(GNNML3_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return GNNML3_OK;
+}
+
 // P: [parts][Ka * Nb] partials
 int gemm_tn_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb,
                       cudaStream_t st) {
     static bool configured[64] = {};
     if (first_use_on_device(configured))
         GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT_SMEM));
+    CUtensorMap mapA, mapB;
+    int rc;
+    if ((rc = tt_make_map(&mapA, A, M, Ka, lda))) return rc;
+    if ((rc = tt_make_map(&mapB, B, M, Nb, ldb))) return rc;
     const int parts = gemm_tn_tc_parts(M);
     int64_t rpc = (M + parts - 1) / parts;
     rpc = (rpc + TT_ROWS - 1) / TT_ROWS * TT_ROWS;
-    k_gemm_tn_tc<<<parts, TT_THREADS, TT_SMEM, st>>>(A, lda, B, ldb, P, M, Ka, Nb, rpc);
+    k_gemm_tn_tc<<<parts, TT_THREADS, TT_SMEM, st>>>(mapA, mapB, P, M, Ka, Nb, rpc);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
