@@ -91,6 +91,9 @@ GNNML3_API int gnnml3_sddmm_k(const int32_t* rowptr, const int32_t* col, const i
  * Tensor-core contractions (mma TF32 with FP32 accumulate; 3xTF32 split for FP32-grade results).
  *   gemm_nn: C[M, Nc] = A[M, Kc] * B[Kc, Nc] (+ bias[Nc]) (+ epilogue)     -- projection  H * W
  *   gemm_tn: C[Ka, Nb] = A[M, Ka]^T * B[M, Nb]                              -- weight gradient, fixed-order split-M
+ *            (Ka <= 32, 8 < Nb <= 256, M >= 8192, 16-byte aligned rows: tcgen05 with MN-major operands fed by TMA;
+ *             Nb <= 8: FP32 FMA kernel; otherwise mma.sync.  Same result contract on every path: deterministic,
+ *             FP32-grade with GNNML3_PREC_3XTF32.  GNNML3_NO_TN_TC=1 in the environment disables the tcgen05 path.)
  * --------------------------------------------------------------------------------------------------- */
 GNNML3_API int gnnml3_gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
                    float* C, int64_t ldc, int64_t M, int Nc, int Kc, int precision, int epilogue, void* stream);
