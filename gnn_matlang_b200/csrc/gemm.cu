@@ -585,10 +585,14 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
     const bool x3 = precision == GNNML3_PREC_3XTF32;
     static const bool no_tc = getenv("GNNML3_NO_TN_TC") != nullptr;
     if (x3 && !no_tc && gemm_tn_tc_ok(A, lda, B, ldb, M, Ka, Nb)) {
-        if ((rc = gemm_tn_tc_launch(A, lda, B, ldb, P, M, Ka, Nb, st))) return rc;
-        const int64_t n = (int64_t)Ka * Nb;
-        k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, gemm_tn_tc_parts(M), n, Nb, C, ldc);
-        GNNML3_LAUNCH_CHECK();
+        // 256 columns of B per launch (one TMEM accumulator set); the partial buffer is reused, launches are stream-ordered
+        for (int c0 = 0; c0 < Nb; c0 += 256) {
+            const int nbc = Nb - c0 < 256 ? Nb - c0 : 256;
+            if ((rc = gemm_tn_tc_launch(A, lda, B + c0, ldb, P, M, Ka, nbc, st))) return rc;
+            const int64_t n = (int64_t)Ka * nbc;
+            k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, gemm_tn_tc_parts(M), n, nbc, C + c0, ldc);
+            GNNML3_LAUNCH_CHECK();
+        }
         return GNNML3_OK;
     }
     if (tn_ba_for(Ka) == 32 && tn_bb_for(Ka, Nb) == 128)

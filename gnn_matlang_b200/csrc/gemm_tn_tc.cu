@@ -182,7 +182,7 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 }
 
 // shape-only eligibility (the workspace query has no pointers); pointer alignment is checked at launch
-bool gemm_tn_tc_shape_ok(int64_t M, int Ka, int Nb) { return Ka >= 1 && Ka <= 32 && Nb > 8 && Nb <= 256 && M >= 8192; }
+bool gemm_tn_tc_shape_ok(int64_t M, int Ka, int Nb) { return Ka >= 1 && Ka <= 32 && Nb > 8 && M >= 8192; }   // Nb > 256: 256-column launches
 int gemm_tn_tc_parts(int64_t M) {
     const int64_t tiles = (M + TT_ROWS - 1) / TT_ROWS;
     return (int)(tiles < kNumSMs ? tiles : kNumSMs);

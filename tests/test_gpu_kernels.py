@@ -168,7 +168,8 @@ def test_gemm_nn(M, Kc, Nc):
 @pytest.mark.parametrize("M,Ka,Nb", [(1, 1, 1), (7, 3, 5), (1000, 25, 240), (5000, 64, 640), (333, 130, 70), (100000, 32, 30),
                                      (2048, 2, 96),
                                      (190001, 32, 4), (3000, 25, 4), (5000, 48, 8), (300, 64, 1),    # narrow (gate) path
-                                     (190001, 32, 256), (20000, 28, 100), (9000, 4, 12), (65536, 32, 64), (8200, 32, 252)])  # tcgen05 path
+                                     (190001, 32, 256), (20000, 28, 100), (9000, 4, 12), (65536, 32, 64), (8200, 32, 252),
+                                     (30000, 32, 320), (12000, 16, 384), (9000, 8, 260)])  # tcgen05 path (last three: several 256-column launches)
 def test_gemm_tn_and_colsum(M, Ka, Nb):
     from gnn_matlang_b200 import ops
     g = torch.Generator().manual_seed(M + Ka + Nb)
