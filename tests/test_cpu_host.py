@@ -99,6 +99,59 @@ def test_collate_is_bit_exact_with_the_oracle():
     assert bool((key[1:] > key[:-1]).all())
 
 
+def test_weight_gradient_workspace_covers_every_kernel_path():
+    """gnnml3_gemm_tn picks its kernel at run time (tcgen05 / narrow FP32 / mma.sync, by shape AND pointer alignment); the
+    shape-only workspace query must cover the partial buffers of all of them (host arithmetic only -- no GPU needed)."""
+    from gnn_matlang_b200 import _lib
+    lib = _lib.load()
+    q = lambda M, Ka, Nb: int(lib.gnnml3_gemm_tn_workspace_bytes(M, Ka, Nb))
+    for M, Ka, Nb in [(189413, 32, 256), (189413, 25, 256), (1000000, 32, 320), (8192, 4, 12), (65536, 32, 64), (30000, 16, 384)]:
+        parts = min(148, (M + 31) // 32)                              # k_gemm_tn_tc: one partial per CTA, 256 columns per launch
+        assert q(M, Ka, Nb) >= parts * Ka * min(Nb, 256) * 4, (M, Ka, Nb)
+    for M, Ka, Nb in [(189413, 32, 4), (3000, 25, 4), (5000, 48, 8), (300, 64, 1), (1, 1, 1)]:
+        assert q(M, Ka, Nb) >= ((M + 255) // 256) * Ka * Nb * 4, (M, Ka, Nb)    # k_gemm_tn_narrow: one partial per 256 rows
+    for M, Ka, Nb in [(1000, 25, 240), (5000, 64, 640), (333, 130, 70), (100000, 32, 30), (2048, 2, 96)]:
+        assert q(M, Ka, Nb) >= Ka * Nb * 4 and q(M, Ka, Nb) % 256 == 0          # split-M mma.sync path: >= one partial
+    assert q(400000, 32, 256) >= q(200000, 32, 256) >= 148 * 32 * 256 * 4
+
+
+def test_collate_property_ragged_and_empty_graphs():
+    """Batch.from_data_list semantics on random ragged inputs, including graphs with a single node
+    and graphs without any support entry: index attributes shifted by the running node count and concatenated along the
+    last dim, everything else along dim 0, `batch` = graph id -- bit-exact against the oracle restatement."""
+    from hypothesis import given, settings, strategies as st
+    from gnn_matlang_b200.batch import collate
+
+    @st.composite
+    def graph_lists(draw):
+        out = []
+        for _ in range(draw(st.integers(1, 9))):
+            n = draw(st.integers(1, 12))
+            e = draw(st.integers(0, 3 * n))
+            seed = draw(st.integers(0, 2 ** 31 - 1))
+            r = np.random.default_rng(seed)
+            ei = np.unique(r.integers(0, n, (2, e)), axis=1) if e else np.zeros((2, 0), np.int64)
+            out.append(dict(x=r.standard_normal((n, 3)).astype(np.float32), edge_index2=ei.astype(np.int64),
+                            edge_attr2=r.standard_normal((ei.shape[1], 4)).astype(np.float32), y=float(r.standard_normal())))
+        return out
+
+    @settings(max_examples=60, deadline=None)
+    @given(graph_lists())
+    def check(recs):
+        a, b = collate(recs), O.collate(recs)
+        for k in ("x", "edge_index2", "edge_attr2", "batch"):
+            assert torch.equal(getattr(a, k), b[k]), k
+        assert a.num_graphs == len(recs) and a.edge_index2.dtype == torch.int64
+        sizes = torch.tensor([r["x"].shape[0] for r in recs])
+        assert torch.equal(a.graph_ptr.long(), torch.cat([torch.zeros(1, dtype=torch.long), sizes.cumsum(0)]))
+        if a.edge_index2.shape[1]:
+            assert int(a.edge_index2.max()) < a.x.shape[0] and int(a.edge_index2.min()) >= 0
+            # every entry stays inside its own graph (block-diagonal supports)
+            assert torch.equal(a.batch[a.edge_index2[0]], a.batch[a.edge_index2[1]])
+
+    check()
+
+
 @pytest.mark.parametrize("kind,kw", [("zinc", dict(recfield=2, dv=2, nfreq=7)),
                                      ("counting", dict(recfield=1, dv=1, nfreq=10, adddegree=True, laplacien=False, addadj=True)),
                                      ("sweep", dict(recfield=1, dv=5, nfreq=9))])
