@@ -1,0 +1,14 @@
+#!/usr/bin/env bash
+# compute-sanitizer pass over the GPU parity tests (run on a B200 box; SURVEY.md section 5 asks for it, the reference has
+# nothing comparable).  memcheck on the kernel-level tests, racecheck on the shared-memory heavy kernels only -- the tools
+# slow kernels down 10-100x, so the large-batch cases are deselected.
+#   usage: gpurun --timeout 1500 -- 'bash tools/sanitize.sh > gpurun_out/sanitize.log 2>&1'
+set -u
+cd "$(dirname "$0")/.."
+SEL='not large and not 100000 and not 190001 and not 65536 and not 150000'
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 \
+    python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fused.py -q -x -k "$SEL"
+echo "memcheck exit code: $?"
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 \
+    python -m pytest tests/test_gpu_kernels.py -q -x -k "(edge_mlp or gemm_tn or segment_pool) and $SEL"
+echo "racecheck exit code: $?"
