@@ -135,7 +135,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "GNNML3 train graphs/s", "value": v, "unit": "graphs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": desc, "graphs_per_step": B},
+        "config": {"workload": args.workload, "reference_script": desc, "graphs_per_step": B},
         "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "%d steps of %d %s-shaped graphs, oracle port of the reference's PyG path on host CPU" % (args.steps, B, args.workload)},
         "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -433,10 +433,10 @@ def main():
             "metric": "GNNML3 train graphs/s", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
-            "config": {"workload": args.workload, "model": desc, "graphs_per_gpu_per_step": B, "global_batch": B * world,
+            "config": {"workload": args.workload, "reference_script": desc, "graphs_per_gpu_per_step": B, "graphs_per_step_all_gpus": B * world,
                        "nodes_per_step_per_gpu": int(N0), "support_entries_per_step_per_gpu": int(E0), "K": pool.K,
                        "edge_attr": pool.supports, "gemm_arithmetic": "3xTF32 (FP32-grade)" if args.precision == "fp32" else "TF32",
-                       "parallelism": "dp%d" % world, "l2_policy": "ring of %d distinct resident batches, %.0f MB in total (> 126 MB L2)" % (args.ring, args.ring * batch_bytes / 1e6),
+                       "sharding": "whole graphs over %d rank(s), one gradient SUM all-reduce per step" % world, "l2_policy": "ring of %d distinct resident batches, %.0f MB in total (> 126 MB L2)" % (args.ring, args.ring * batch_bytes / 1e6),
                        "timed_step": "csr_build + fwd + loss + bwd + (allreduce) + Adam"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "host_enqueue_ms_per_step": host_ms, "kernel_ms_per_step": breakdown, "final_loss": float(loss_t.item())}), flush=True)
