@@ -209,3 +209,15 @@ def test_data_parallel_step_equals_single_process(tmp_path):
     dp, single = torch.load(tmp)
     for a, b in zip(dp, single):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_launch_list_summary_matches_the_committed_profile():
+    """profiles/r01_ncu_launches_zinc_one_step_final.csv is tools/summarise_launches.py applied to the committed raw ncu
+    launch list (6 captured steps): per-kernel totals of the last step, shares summing to 1."""
+    raw = os.path.join(ROOT, "profiles", "r01_ncu_launches_zinc_steps2_final_raw.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarise_launches.py"), raw, "6"],
+                         capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(ROOT, "profiles", "r01_ncu_launches_zinc_one_step_final.csv")).read()
+    rows = [l.split(",") for l in out.strip().splitlines()[1:]]
+    assert rows[-1][0] == "TOTAL" and abs(sum(float(r[-1]) for r in rows[:-1]) - 1.0) < 5e-3
+    assert any("k_fused_agg_proj" in l for l in out.splitlines()[1:3])            # the dominant kernel the roofline is quoted on
