@@ -181,24 +181,6 @@ def test_gemm_tn_and_colsum(M, Ka, Nb):
     assert_close(ops.colsum(B.to(dev())), B.double().sum(0), name="colsum")
 
 
-def test_gemm_tn_column_block_views():
-    """Operands that are column-block views of wider buffers (row stride > width, as the layer entry points pass them): the
-    columns between the width and the row stride hold other data and must not leak into the contraction -- on the tcgen05
-    path they are outside the TMA tensor map (zero-filled), on the other paths they are masked."""
-    from gnn_matlang_b200 import ops
-    g = torch.Generator().manual_seed(9)
-    M = 20000
-    for Ka, lda, Nb, ldb in [(25, 28, 256, 260), (32, 36, 100, 128), (25, 28, 4, 8)]:
-        abuf = torch.full((M, lda), 3.0)
-        bbuf = torch.full((M, ldb), -5.0)
-        abuf[:, :Ka] = torch.randn(M, Ka, generator=g)
-        bbuf[:, :Nb] = torch.randn(M, Nb, generator=g)
-        A, B = abuf.to(dev())[:, :Ka], bbuf.to(dev())[:, :Nb]
-        assert A.stride(0) == lda and B.stride(0) == ldb
-        out = ops.gemm_tn(A, B)
-        assert_close(out, abuf[:, :Ka].double().t() @ bbuf[:, :Nb].double(), name="gemm_tn views %d/%d x %d/%d" % (Ka, lda, Nb, ldb))
-
-
 def test_cpu_tensors_are_refused():
     from gnn_matlang_b200.libs.spect_conv import SpectConv
     m = SpectConv(4, 4, 2, selfconn=False)
