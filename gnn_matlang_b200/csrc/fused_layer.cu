@@ -855,6 +855,7 @@ static int g_fl_nagg16 = [] {
 }();
 
 extern "C" int gnnml3_fused_supported(int K, int Kstride, int F, int Nc, int Fs, int self_mode, int Ns) {
+    if (gnnml3_fused_ts_supported(K, Kstride, F, Nc, Fs, self_mode, Ns)) return 1;
     const int kt = fl_kt_for(K);
     if (kt == 0 || F < 1 || Nc < 1 || Nc > 64) return 0;
     if (((F + 31) / 32) * K > 24) return 0;               // accumulation chain per tile kept short (TMEM adds truncate)
@@ -867,7 +868,9 @@ extern "C" int gnnml3_fused_supported(int K, int Kstride, int F, int Nc, int Fs,
 
 extern "C" size_t gnnml3_fused_workspace_bytes(int K, int F, int Nc, int self_mode) {
     const int nfh = cdiv(F, 32);
-    return align_up((size_t)(nfh * K + (self_mode != 0 ? 1 : 0)) * 2 * fl_bnh_for(Nc) * 128, 256);
+    const size_t a = align_up((size_t)(nfh * K + (self_mode != 0 ? 1 : 0)) * 2 * fl_bnh_for(Nc) * 128, 256);
+    const size_t b = gnnml3_fused_ts_workspace_bytes(K, Nc, self_mode);
+    return a > b ? a : b;
 }
 
 constexpr size_t FL_SMEM_MAX = 227 * 1024;                                              // opt-in limit per CTA on sm_100
@@ -932,6 +935,18 @@ static int fl_launch2(const CUtensorMap& mW, FLParams& P, size_t smem, cudaStrea
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
+
+namespace gnnml3 {
+// tensor-memory generation of the kernel (fused_layer_ts.cu)
+int fused_ts_run(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea, int Kstride, int K, const float* X,
+                 int64_t ldx, int F, const float* S, int64_t lds, int Fs, int self_mode, const float* Bmain, int64_t ldb,
+                 const float* Bself, int64_t ldbs, int Ns, const float* bias, const float* bias_s, int64_t N, int Nc, float* out,
+                 int64_t ldo, float* aux, int64_t ldaux, int G, int epilogue, float* hout, int64_t ldh, const int32_t* tilewin,
+                 void* workspace, size_t workspace_bytes, unsigned long long* dbg, cudaStream_t st);
+void fused_path_count(int which);
+}
+extern "C" int gnnml3_fused_ts_supported(int K, int Kstride, int F, int Nc, int Fs, int self_mode, int Ns);
+extern "C" size_t gnnml3_fused_ts_workspace_bytes(int K, int Nc, int self_mode);
 
 // Weight planes stay resident in shared memory when at least 3 H-plane stages fit beside them; otherwise every k-block's
 // plane is streamed from L2 into its stage (large K * F: L2-bandwidth bound).
@@ -1031,7 +1046,8 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
                                      int Fs, int self_mode, const float* Bmain, int64_t ldb, const float* Bself,
                                      int64_t ldbs, int Ns, const float* bias, const float* bias_s, int64_t N, int Nc,
                                      float* out, int64_t ldo, float* aux, int64_t ldaux, int G, int epilogue,
-                                     float* hout, int64_t ldh, void* workspace, size_t workspace_bytes, void* stream_) {
+                                     float* hout, int64_t ldh, const int32_t* tilewin, void* workspace, size_t workspace_bytes,
+                                     void* stream_) {
     GNNML3_REQUIRE(N > 0 && N < (1ll << 31) - 256, "fused_agg_proj: bad N");
     GNNML3_REQUIRE(rowptr && col && ea && X && Bmain && out && workspace, "fused_agg_proj: NULL pointer");
     GNNML3_REQUIRE(gnnml3_fused_supported(K, Kstride, F, Nc, Fs, self_mode, Ns), "fused_agg_proj: unsupported shape "
@@ -1050,8 +1066,35 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
     if (workspace_bytes < gnnml3_fused_workspace_bytes(K, F, Nc, self_mode))
         return set_err(GNNML3_ERR_WORKSPACE, "fused_agg_proj: workspace too small");
     cudaStream_t st = (cudaStream_t)stream_;
+    if (g_fl_debug && !g_fl_dbg) {
+        GNNML3_CUDA(cudaMalloc(&g_fl_dbg, 16 * sizeof(unsigned long long)));
+        GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 16 * sizeof(unsigned long long)));
+    }
+    if (gnnml3_fused_ts_supported(K, Kstride, F, Nc, Fs, self_mode, Ns) && g_fl_slot_mode == 0) {
+        // tensor-memory generation (fused_layer_ts.cu): one 32-wide feature block per support, K % 2 == 0
+        FLProfRec rec;
+        if (g_fl_prof_on) {
+            cudaEventCreate(&rec.a);
+            cudaEventCreate(&rec.b);
+            const double m[9] = {(double)N, (double)K, (double)F, (double)Nc, (double)Fs, (double)self_mode,
+                                 (double)(self_mode == 1 ? 2 * G : 0), (double)G, eperm ? 1.0 : 0.0};
+            for (int i = 0; i < 9; ++i) rec.meta[i] = m[i];
+            cudaEventRecord(rec.a, st);
+        }
+        const int rc = fused_ts_run(rowptr, col, eperm, ea, Kstride, K, X, ldx, F, S, lds, Fs, self_mode, Bmain, ldb, Bself, ldbs, Ns, bias,
+                                    bias_s, N, Nc, out, ldo, aux, ldaux, G, epilogue, hout, ldh, tilewin, workspace, workspace_bytes,
+                                    g_fl_dbg, st);
+        if (g_fl_prof_on) {
+            cudaEventRecord(rec.b, st);
+            g_fl_prof.push_back(rec);
+        }
+        if (rc == GNNML3_OK) fused_path_count(0);
+        return rc;
+    }
+    fused_path_count(1);
     const int BNH = fl_bnh_for(Nc);
     int KT = fl_kt_for(K);
+    GNNML3_REQUIRE(KT != 0, "fused_agg_proj: no shared-memory-plane kernel for K=%d", K);
     const int nfh = cdiv(F, 32);
     if (K == 8 && g_fl_split && nfh == 1 && Kstride % 4 == 0 && !g_fl_no_slot) KT = 4;
     if (K == 8 && g_fl_wide) KT = 4;
@@ -1074,10 +1117,6 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
     P.bias = bias; P.bias_s = bias_s; P.out = out; P.ldo = ldo; P.Nc = Nc; P.aux = aux; P.ldaux = ldaux; P.G = G;
     P.epi = epilogue;
     P.hout = hout; P.ldh = ldh;
-    if (g_fl_debug && !g_fl_dbg) {
-        GNNML3_CUDA(cudaMalloc(&g_fl_dbg, 16 * sizeof(unsigned long long)));
-        GNNML3_CUDA(cudaMemset(g_fl_dbg, 0, 16 * sizeof(unsigned long long)));
-    }
     P.dbg = g_fl_dbg;
     if (g_fl_nagg16 && K == 8 && Kstride % 4 == 0 && g_fl_no_slot) {     // 16 aggregator warps, 4 supports per pass, 128-row tiles
         if (BNH == 32) return fl_launch<4, 32, 16>(mW, P, st);

@@ -1,0 +1,723 @@
+// Fused aggregate + project kernel, second generation: the aggregate lives in TENSOR MEMORY.
+//
+// Same contract as fused_layer.cu (reference libs/spect_conv.py:70-80,93-94 and :208-212):
+//     conv[t, :] = sum_k ( sum_{e: dst_e = t} ea[e, k] * x[src_e, :] ) W_k  + bias            (SpectConv)
+//     y[t, :]    = [ relu(conv[t, :]) || tanh(x[t] W11^T + b11) * tanh(x[t] W12^T + b12) ]    (ML3Layer)
+// What changed, and why (measured on B200, profiles/r02_tmem_probe.txt and the round-1 ncu captures):
+//   * the round-1 kernel wrote every 32-column block of the aggregate H twice into shared memory (raw + residual plane,
+//     8 bytes per element) and the tensor core read both back: ~0.9 MB of shared-memory traffic per 128-row tile, more than
+//     anything else the SM did.  Here the aggregator warps hand H to the tensor core through TENSOR MEMORY: tcgen05.st
+//     (16x64b.x16: two threads per row, each thread owns one row's odd or even columns) writes the raw FP32 block (the
+//     tensor core truncates it to TF32 itself = the hi part) and the residual block lo = a - trunc(a) into a ring of four
+//     64-column slots, and tcgen05.mma reads its A operand from there (A in TMEM, M = 128 tile rows on the 128 lanes).
+//     Shared memory now only holds the weights (B operand, N side) and the staged source rows.
+//   * tcgen05.mma costs max(45, N/2) cycles (not "143 whatever the shape": that was the round-1 probe's own loop).  With
+//     the rows on M and the weights on N, a k-step is  D[:, 0:2B] += H_raw [W_hi | W_lo]^T  (N = 2B)  followed by
+//     D[:, B:2B] += H_lo W_hi^T  (N = B):  ~90 cycles per 128 rows instead of 128, and no wasted lo x lo product.
+//     The hi x hi sum keeps its own accumulator columns (chain of 4 * K additions per tile, as before).
+//   * the gathered source rows come from SHARED MEMORY: a batched disjoint graph only has edges inside a graph, so the
+//     sources of a 128-row tile lie in a window of at most 128 + 2 * (largest graph - 1) consecutive rows of X.  The
+//     per-tile window [first, last] is part of the graph plan (gnnml3_tile_windows); a producer thread brings the window
+//     in with ONE TMA box load (256 rows x 128 B, 128B-swizzled, zero-filled outside X), one tile ahead, double buffered.
+//     Each source row is then read from L2 once per tile instead of once per edge and pass (5.6x less L2 traffic on the
+//     ZINC batches), and the dependent chain col -> x row ends in a 29-cycle LDS instead of a ~300-cycle L2 round trip.
+//     Tiles whose window does not fit (general graphs) gather from global memory as before -- same arithmetic.
+// Summation order per row = edge order of the CSR row (the reference's CPU scatter order); no atomics.
+#include "tc_common.cuh"
+
+#include <vector>
+
+namespace gnnml3 {
+
+constexpr int TS_ROWS = 128;                     // dst rows per tile = TMEM lanes = MMA M
+constexpr int TS_WIN_ROWS = 256;                 // rows of the staged source window (one TMA box)
+constexpr int TS_NSLOT = 4;                      // ring of H slots in tensor memory (64 columns each: raw | lo)
+constexpr int TS_THREADS = 512;                  // warps 0-3 epilogue | 4 producer | 5 MMA | 6,7 idle | 8-15 aggregators
+constexpr int TS_AGG0 = 8;
+
+struct TSParams {
+    const int* rowptr;
+    const int* col;
+    const int* eperm;
+    const float* ea;
+    int Kstride, K;
+    const float* X;
+    int64_t ldx;
+    int F;
+    const float* S;
+    int64_t lds;
+    int Fs;
+    int self_mode;          // 0 none | 1 own output columns (ML3 gates) | 2 accumulates into the main columns
+    int64_t N;
+    int n_tiles;
+    int nkb_main;           // = K (one 32-wide feature block per support)
+    const int2* tilewin;    // [n_tiles] {first, last + 1} source row of the tile's CSR slots; NULL: gather from global memory
+    int win_rows;           // rows of the TMA box (<= TS_WIN_ROWS)
+    const float* bias;
+    const float* bias_s;
+    float* out;
+    int64_t ldo;
+    int Nc;
+    float* aux;
+    int64_t ldaux;
+    int G;
+    int epi;                // 0 plain (+bias) | 1 ml3: relu on the main columns, tanh*tanh gating on the self columns
+    float* hout;            // optional copy of the aggregate [N, ldh]: support k at column 32 k, self block behind
+    int64_t ldh;
+    unsigned long long* dbg;
+};
+
+__device__ __forceinline__ void ts_mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(32);
+    }
+}
+
+__device__ __forceinline__ float ts_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+__device__ __forceinline__ float4 ts_lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+// 16 TMEM lanes x 32 columns: thread T owns lane 8 * (T & 1) + (T >> 2) and the 16 columns ((T >> 1) & 1) + 2 j
+// (layout pinned on the B200 by scratch/tmem_probe.cu)
+__device__ __forceinline__ void ts_st_16x64b_x16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.16x64b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+                 "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void ts_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, TF32 inputs (truncated by the tensor core), FP32 accumulate
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int KT>
+__device__ __forceinline__ void ts_load_w(const float* __restrict__ p, float (&w)[KT]) {
+    if constexpr (KT == 4) {
+        const float4 v = ldg4(p);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else if constexpr (KT == 2) {
+        const float2 v = ldg2(p);
+        w[0] = v.x; w[1] = v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) w[k] = __ldg(p + k);
+    }
+}
+
+template <int KT>
+__device__ __forceinline__ void ts_fma(float (&acc)[KT][16], const float (&w)[KT], const float4& x0, const float4& x1, const float4& x2,
+                                       const float4& x3) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        acc[k][0] = fmaf(w[k], x0.x, acc[k][0]);
+        acc[k][1] = fmaf(w[k], x0.y, acc[k][1]);
+        acc[k][2] = fmaf(w[k], x0.z, acc[k][2]);
+        acc[k][3] = fmaf(w[k], x0.w, acc[k][3]);
+        acc[k][4] = fmaf(w[k], x1.x, acc[k][4]);
+        acc[k][5] = fmaf(w[k], x1.y, acc[k][5]);
+        acc[k][6] = fmaf(w[k], x1.z, acc[k][6]);
+        acc[k][7] = fmaf(w[k], x1.w, acc[k][7]);
+        acc[k][8] = fmaf(w[k], x2.x, acc[k][8]);
+        acc[k][9] = fmaf(w[k], x2.y, acc[k][9]);
+        acc[k][10] = fmaf(w[k], x2.z, acc[k][10]);
+        acc[k][11] = fmaf(w[k], x2.w, acc[k][11]);
+        acc[k][12] = fmaf(w[k], x3.x, acc[k][12]);
+        acc[k][13] = fmaf(w[k], x3.y, acc[k][13]);
+        acc[k][14] = fmaf(w[k], x3.z, acc[k][14]);
+        acc[k][15] = fmaf(w[k], x3.w, acc[k][15]);
+    }
+}
+
+#ifdef FL_PROFILE
+#define TS_CNT(...) __VA_ARGS__
+#else
+#define TS_CNT(...)
+#endif
+
+// KT = supports per register pass (K % KT == 0).  BNH = 32: Nc <= 32 (+ optional gate block), 64: Nc <= 64.
+// Tensor-memory map (512 columns): accumulator buffers at 0 and 128 (main [0, 2 BNH): hi-weight | lo-weight partial sums,
+// gates [64, 128) when BNH = 32), H slots at 256 + 64 s (raw columns 0-31, residual columns 32-63).
+// Column c of a slot holds feature 16 * (c & 1) + (c >> 1) of the 32-wide block (the store layout gives a thread the even
+// or the odd columns; it gathers features 0-15 or 16-31): the weight planes are permuted the same way (k_ts_prep_weights).
+template <int KT, int BNH>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+k_fused_ts(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const __grid_constant__ TSParams P) {
+    constexpr int WPLANE = 2 * BNH * 128;               // bytes of one weight plane: rows [W_hi^T ; W_lo^T] x 32 k-columns
+    constexpr uint32_t ID_FULL = make_idesc_tf32_mn(128, 2 * BNH), ID_HALF = make_idesc_tf32_mn(128, BNH);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nkb_total = P.nkb_main + (P.self_mode != 0 ? 1 : 0);
+    uint8_t* xbuf = smem;                                                   // [2][TS_WIN_ROWS * 128]
+    uint8_t* wres = smem + 2 * TS_WIN_ROWS * 128;                           // [nkb_total][WPLANE]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wres + (size_t)nkb_total * WPLANE);
+    uint64_t* full = bars;                       // [4]  slot written by the 8 aggregator warps      -> MMA
+    uint64_t* empty = bars + 4;                  // [4]  MMAs that read the slot have retired         -> aggregators
+    uint64_t* tfull = bars + 8;                  // [2]  tile accumulator complete                    -> epilogue
+    uint64_t* tempty = bars + 10;                // [2]  accumulator drained                          -> MMA
+    uint64_t* wfull = bars + 12;                 // [1]  weight planes landed                         -> MMA
+    uint64_t* xfull = bars + 13;                 // [2]  source window landed                         -> aggregators
+    uint64_t* xempty = bars + 15;                // [2]  window no longer read                        -> producer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_NSLOT; ++s) {
+            mbar_init(full + s, 8);
+            mbar_init(empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull + b, 1);
+            mbar_init(tempty + b, 4);
+            mbar_init(xfull + b, 1);
+            mbar_init(xempty + b, 8);
+        }
+        mbar_init(wfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // =================================================================== producer: weight planes once, source windows per tile
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wfull, (uint32_t)nkb_total * WPLANE);
+            for (int kb = 0; kb < nkb_total; ++kb) tma_load_2d(wres + (size_t)kb * WPLANE, &mapW, wfull, 0, kb * 2 * BNH);
+            if (P.tilewin) {
+                uint32_t ts = 0;
+                const uint32_t xbytes = (uint32_t)P.win_rows * 128u;
+                for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                    const int2 w = __ldg(P.tilewin + tile);
+                    if (w.y > w.x && w.y - w.x <= P.win_rows) {
+                        const uint32_t b = ts & 1;
+                        ts_mbar_wait_idle(xempty + b, ((ts >> 1) & 1) ^ 1);
+                        mbar_arrive_expect_tx(xfull + b, xbytes);
+                        tma_load_2d(xbuf + (size_t)b * TS_WIN_ROWS * 128, &mapX, xfull + b, 0, w.x);
+                        ++ts;
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // =================================================================== MMA issuer (one lane)
+        if (lane == 0) {
+            ts_mbar_wait_idle(wfull, 0);
+            uint32_t tt = 0, s = 0, sph = 0;
+            const uint32_t wres0 = smem_u32(wres);
+            TS_CNT(long long c_full = 0, c_tempty = 0; const long long c_begin = clock64();)
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
+                const uint32_t buf = tt & 1;
+                TS_CNT(long long c0 = clock64();)
+                ts_mbar_wait_idle(tempty + buf, ((tt >> 1) & 1) ^ 1);
+                TS_CNT(c_tempty += clock64() - c0;)
+                tc_fence_after();
+                const uint32_t d_main = tmem_base + buf * 128;
+                for (int kb = 0; kb < nkb_total; ++kb) {
+                    TS_CNT(c0 = clock64();)
+                    mbar_wait(full + s, sph);
+                    TS_CNT(c_full += clock64() - c0;)
+                    tc_fence_after();
+                    const uint32_t a_raw = tmem_base + 256 + s * 64, a_lo = a_raw + 32;
+                    const uint64_t dw = make_kmajor_sw128_desc(wres0 + (uint32_t)kb * WPLANE);
+                    const bool gate = P.self_mode == 1 && kb == P.nkb_main;
+                    const uint32_t d = gate ? d_main + 64 : d_main;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);     // 8 TF32 = 32 bytes along K inside the swizzled row
+                        umma_tf32_ts(d, a_raw + 8 * k, dw + adv, ID_FULL, ((gate || kb == 0) && k == 0) ? 0u : 1u);
+                        umma_tf32_ts(d + BNH, a_lo + 8 * k, dw + adv, ID_HALF, 1u);
+                    }
+                    umma_commit(empty + s);
+                    if (++s == TS_NSLOT) {
+                        s = 0;
+                        sph ^= 1;
+                    }
+                }
+                umma_commit(tfull + buf);
+            }
+            TS_CNT(if (P.dbg) {
+                atomicAdd(P.dbg + 3, (unsigned long long)c_full);
+                atomicAdd(P.dbg + 4, (unsigned long long)c_tempty);
+                atomicAdd(P.dbg + 5, (unsigned long long)(clock64() - c_begin));
+            })
+        }
+    } else if (warp < 4) {
+        // =================================================================== epilogue: thread = tile row = TMEM lane
+        const int Fo = P.Nc, G = P.G;
+        const bool has_gates = BNH == 32 && P.self_mode == 1;
+        const bool vec_out = (P.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
+        uint32_t tt = 0;
+        TS_CNT(long long c_tfull = 0; const long long c_begin = clock64();)
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tt) {
+            const uint32_t buf = tt & 1;
+            TS_CNT(const long long cw = clock64();)
+            ts_mbar_wait_idle(tfull + buf, (tt >> 1) & 1);
+            TS_CNT(c_tfull += clock64() - cw;)
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 128;
+            const int64_t r = (int64_t)tile * TS_ROWS + warp * 32 + lane;
+            const bool live = r < P.N;
+            float* orow = P.out + (live ? r : 0) * P.ldo;
+#pragma unroll
+            for (int c0 = 0; c0 < BNH; c0 += 32) {
+                float vh[32], vl[32];
+                tmem_ld32(taddr + c0, vh);
+                tmem_ld32(taddr + BNH + c0, vl);
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float o = vh[i] + vl[i];
+                        if (P.bias && c0 + i < Fo) o += __ldg(P.bias + c0 + i);
+                        if (P.epi == 1) o = fmaxf(o, 0.f);
+                        vh[i] = o;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (vec_out && c0 + i + 3 < Fo) {
+                            *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(vh[i], vh[i + 1], vh[i + 2], vh[i + 3]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (c0 + i + k < Fo) orow[c0 + i + k] = vh[i + k];
+                        }
+                    }
+                }
+            }
+            if (has_gates) {
+                // gate accumulator: p1_j in columns 64 + j (hi weights) / 96 + j (lo weights), p2_j in 80 + j / 112 + j
+                float g1h[16], g2h[16], g1l[16], g2l[16];
+                tmem_ld16(taddr + 64, g1h);
+                tmem_ld16(taddr + 80, g2h);
+                tmem_ld16(taddr + 96, g1l);
+                tmem_ld16(taddr + 112, g2l);
+                if (live) {
+                    float* ax = P.aux + r * P.ldaux;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < G) {
+                            float p1 = g1h[j] + g1l[j], p2 = g2h[j] + g2l[j];
+                            if (P.bias_s) {
+                                p1 += __ldg(P.bias_s + j);
+                                p2 += __ldg(P.bias_s + G + j);
+                            }
+                            const float t1 = tanh_fast(p1), t2 = tanh_fast(p2);
+                            orow[Fo + j] = t1 * t2;
+                            ax[j] = t1;
+                            ax[G + j] = t2;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + buf);
+        }
+        TS_CNT(if (P.dbg && lane == 0) {
+            atomicAdd(P.dbg + 6, (unsigned long long)c_tfull);
+            atomicAdd(P.dbg + 7, (unsigned long long)(clock64() - c_begin));
+        })
+    } else if (warp >= TS_AGG0) {
+        // =================================================================== aggregators (8 warps x 16 rows, 2 threads per row)
+        const int aw = warp - TS_AGG0;
+        const int lrow = 32 * (aw & 3) + 16 * (aw >> 2) + 8 * (lane & 1) + (lane >> 2);     // tile row = TMEM lane of this thread
+        const int p = (lane >> 1) & 1;                                                      // features 16 p .. 16 p + 15
+        const uint32_t lane_addr = (uint32_t)(32 * (aw & 3) + 16 * (aw >> 2)) << 16;
+        const int* __restrict__ rowptr = P.rowptr;
+        const int* __restrict__ col = P.col;
+        const int* __restrict__ eperm = P.eperm;
+        const float* __restrict__ ea = P.ea;
+        const float* __restrict__ X = P.X;
+        const int64_t ldx = P.ldx;
+        const int Kstride = P.Kstride;
+        const int F = P.F;
+        const uint32_t xbuf32 = smem_u32(xbuf);
+        uint32_t st_i = 0, st_ph = 1, ts = 0;
+        TS_CNT(long long c_gather = 0, c_wait = 0, c_xwait = 0; const long long c_begin = clock64();)
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            const int64_t row = (int64_t)tile * TS_ROWS + lrow;
+            int rs = 0, re = 0;
+            if (row < P.N) {
+                rs = __ldg(rowptr + row);
+                re = __ldg(rowptr + row + 1);
+            }
+            bool staged = false;
+            int win0 = 0;
+            uint32_t xb32 = 0, xb = 0;
+            if (P.tilewin) {
+                const int2 w = __ldg(P.tilewin + tile);
+                staged = w.y > w.x && w.y - w.x <= P.win_rows;
+                win0 = w.x;
+            }
+            if (staged) {
+                xb = ts & 1;
+                xb32 = xbuf32 + xb * (uint32_t)(TS_WIN_ROWS * 128);
+                TS_CNT(const long long cx = clock64();)
+                mbar_wait(xfull + xb, (ts >> 1) & 1);
+                TS_CNT(c_xwait += clock64() - cx;)
+                ++ts;
+            }
+            TS_CNT(long long cg0 = clock64();)
+            for (int k0 = 0; k0 < P.K; k0 += KT) {
+                float acc[KT][16];
+#pragma unroll
+                for (int k = 0; k < KT; ++k)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[k][i] = 0.f;
+                // software pipeline over the row's CSR slots: indices two slots ahead, edge weights one slot ahead
+                int sidx_n = 0, sidx_nn = 0, eidx_nn = 0;
+                float w_n[KT];
+#pragma unroll
+                for (int k = 0; k < KT; ++k) w_n[k] = 0.f;
+                if (rs < re) {
+                    sidx_n = __ldg(col + rs);
+                    const int e0 = eperm ? __ldg(eperm + rs) : rs;
+                    ts_load_w<KT>(ea + (int64_t)e0 * Kstride + k0, w_n);
+                    if (rs + 1 < re) {
+                        sidx_nn = __ldg(col + rs + 1);
+                        eidx_nn = eperm ? __ldg(eperm + rs + 1) : rs + 1;
+                    }
+                }
+                for (int p0 = rs; p0 < re; ++p0) {
+                    const int sidx = sidx_n;
+                    float w[KT];
+#pragma unroll
+                    for (int k = 0; k < KT; ++k) w[k] = w_n[k];
+                    sidx_n = sidx_nn;
+                    if (p0 + 1 < re) ts_load_w<KT>(ea + (int64_t)eidx_nn * Kstride + k0, w_n);
+                    if (p0 + 2 < re) {
+                        sidx_nn = __ldg(col + p0 + 2);
+                        eidx_nn = eperm ? __ldg(eperm + p0 + 2) : p0 + 2;
+                    }
+                    float4 x0, x1, x2, x3;
+                    if (staged) {
+                        const int s = sidx - win0;
+                        const uint32_t ra = xb32 + (uint32_t)s * 128u;
+                        const uint32_t sw = (uint32_t)(s & 7) << 4;
+                        const uint32_t c0 = (uint32_t)p << 6;
+                        x0 = ts_lds128(ra + ((c0 + 0u) ^ sw));
+                        x1 = ts_lds128(ra + ((c0 + 16u) ^ sw));
+                        x2 = ts_lds128(ra + ((c0 + 32u) ^ sw));
+                        x3 = ts_lds128(ra + ((c0 + 48u) ^ sw));
+                    } else {
+                        const float* xr = X + (int64_t)sidx * ldx + 16 * p;
+                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                        x0 = 16 * p + 0 < F ? ldg4(xr + 0) : z;
+                        x1 = 16 * p + 4 < F ? ldg4(xr + 4) : z;
+                        x2 = 16 * p + 8 < F ? ldg4(xr + 8) : z;
+                        x3 = 16 * p + 12 < F ? ldg4(xr + 12) : z;
+                    }
+                    ts_fma<KT>(acc, w, x0, x1, x2, x3);
+                }
+                if (P.hout && row < P.N) {           // side output for the weight-gradient contraction of the backward
+                    float* hr = P.hout + row * P.ldh + (int64_t)k0 * 32 + 16 * p;
+#pragma unroll
+                    for (int k = 0; k < KT; ++k)
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) st_na4(hr + k * 32 + i, make_float4(acc[k][i], acc[k][i + 1], acc[k][i + 2], acc[k][i + 3]));
+                }
+                __syncwarp();
+                TS_CNT(c_gather += clock64() - cg0;)
+                if (staged && k0 + KT >= P.K) {      // last pass over the window: hand the buffer back to the producer
+                    if (lane == 0) mbar_arrive(xempty + xb);
+                }
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    TS_CNT(const long long cw = clock64();)
+                    mbar_wait(empty + st_i, st_ph);
+                    TS_CNT(c_wait += clock64() - cw;)
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + lane_addr + 256 + st_i * 64;
+                    float lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) lo[i] = ts_lo(acc[k][i]);
+                    ts_st_16x64b_x16(ta, acc[k]);
+                    ts_st_16x64b_x16(ta + 32, lo);
+                    ts_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full + st_i);
+                    if (++st_i == TS_NSLOT) {
+                        st_i = 0;
+                        st_ph ^= 1;
+                    }
+                }
+                TS_CNT(cg0 = clock64();)
+            }
+            if (P.self_mode != 0) {
+                float sv[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sv[i] = 0.f;
+                if (row < P.N) {
+                    const float* sr = P.S + row * P.lds + 16 * p;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        if (16 * p + i < P.Fs) {
+                            const float4 t = ldg4(sr + i);
+                            sv[i] = t.x; sv[i + 1] = t.y; sv[i + 2] = t.z; sv[i + 3] = t.w;
+                        }
+                    }
+                    if (P.hout) {
+                        float* hr = P.hout + row * P.ldh + (int64_t)P.K * 32 + 16 * p;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) st_na4(hr + i, make_float4(sv[i], sv[i + 1], sv[i + 2], sv[i + 3]));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) lo[i] = ts_lo(sv[i]);
+                mbar_wait(empty + st_i, st_ph);
+                tc_fence_after();
+                const uint32_t ta = tmem_base + lane_addr + 256 + st_i * 64;
+                ts_st_16x64b_x16(ta, sv);
+                ts_st_16x64b_x16(ta + 32, lo);
+                ts_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + st_i);
+                if (++st_i == TS_NSLOT) {
+                    st_i = 0;
+                    st_ph ^= 1;
+                }
+            }
+        }
+        TS_CNT(if (P.dbg && lane == 0) {
+            atomicAdd(P.dbg + 0, (unsigned long long)c_gather);
+            atomicAdd(P.dbg + 1, (unsigned long long)c_wait);
+            atomicAdd(P.dbg + 2, (unsigned long long)(clock64() - c_begin));
+            atomicAdd(P.dbg + 8, (unsigned long long)c_xwait);
+        })
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// Weight planes of the TS kernel: one [2 BNH rows x 32 k-columns] K-major plane per k-block (kb = k for the K supports,
+// kb = K for the self block).  Plane row n < BNH: hi = RN-TF32(w) of output column n; row BNH + n: lo = w - hi.  Plane
+// column c holds feature f(c) = 16 * (c & 1) + (c >> 1) of the block (the tensor-memory column order of the aggregators).
+// Self plane: mode 2 -> Bself [Fs, Nc]; mode 1 -> the gate weights Bself [Fs, Ns = 2G] = [W11^T | W12^T]: p1_j in plane row j,
+// p2_j in plane row 16 + j (so the epilogue pairs accumulator columns j and 16 + j whatever G is).
+__global__ void k_ts_prep_weights(const float* __restrict__ Bmain, int64_t ldb, int K, int F, int Nc, int BNH,
+                                  const float* __restrict__ Bself, int64_t ldbs, int Fs, int Ns, int self_mode,
+                                  float* __restrict__ planes) {
+    const int nkb_total = K + (self_mode != 0 ? 1 : 0);
+    const int MR = 2 * BNH;
+    const int total = nkb_total * MR * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int kb = i / (MR * 32), m = (i / 32) % MR, c = i % 32;
+        const int n = m % BNH;
+        const bool is_lo = m >= BNH;
+        const int f = 16 * (c & 1) + (c >> 1);
+        float v = 0.f;
+        if (kb < K) {
+            if (f < F && n < Nc) v = __ldg(Bmain + ((int64_t)kb * F + f) * ldb + n);
+        } else if (self_mode == 2) {
+            if (f < Fs && n < Nc) v = __ldg(Bself + (int64_t)f * ldbs + n);
+        } else {
+            const int j = n & 15, which = n >> 4, G = Ns >> 1;      // plane row j: p1_j, row 16 + j: p2_j
+            if (f < Fs && j < G) v = __ldg(Bself + (int64_t)f * ldbs + which * G + j);
+        }
+        const float h = tf32_rn(v);
+        planes[i] = is_lo ? v - h : h;
+    }
+}
+
+// Source window of every tile of `rows_per_tile` CSR rows: win[t] = {min col, max col + 1} over the tile's slots
+// ({0, 0} for a tile without slots).  Integer work, exact.
+__global__ void k_tile_windows(const int* __restrict__ rowptr, const int* __restrict__ col, int64_t N, int rows_per_tile, int n_tiles,
+                               int2* __restrict__ win) {
+    const int tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    const int64_t r0 = (int64_t)tile * rows_per_tile;
+    const int64_t r1 = r0 + rows_per_tile < N ? r0 + rows_per_tile : N;
+    const int e0 = __ldg(rowptr + r0), e1 = __ldg(rowptr + r1);
+    int lo = 0x7fffffff, hi = -1;
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int c = __ldg(col + e);
+        lo = c < lo ? c : lo;
+        hi = c > hi ? c : hi;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const int l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    __shared__ int slo[8], shi[8];
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            lo = slo[w] < lo ? slo[w] : lo;
+            hi = shi[w] > hi ? shi[w] : hi;
+        }
+        win[tile] = hi >= 0 ? make_int2(lo, hi + 1) : make_int2(0, 0);
+    }
+}
+
+}  // namespace gnnml3
+
+using namespace gnnml3;
+
+extern "C" int gnnml3_tile_rows(void) { return TS_ROWS; }
+
+extern "C" int gnnml3_tile_windows(const int32_t* rowptr, const int32_t* col, int64_t N, int32_t* win, void* stream) {
+    GNNML3_REQUIRE(N > 0 && rowptr && win, "tile_windows: bad arguments");
+    const int n_tiles = cdiv(N, TS_ROWS);
+    k_tile_windows<<<n_tiles, 128, 0, (cudaStream_t)stream>>>(rowptr, col, N, TS_ROWS, n_tiles, reinterpret_cast<int2*>(win));
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+static const bool g_ts_enabled = [] {
+    const char* e = getenv("GNNML3_FUSED_TS");
+    return !(e && e[0] == '0');
+}();
+static int g_ts_runtime_enabled = 1;
+
+// which kernel gnnml3_fused_agg_proj dispatched to since the last reset: [0] tensor-memory kernel, [1] round-1 shared-memory
+// plane kernel; the Python side adds the counts of the two-kernel fallback (bench.py prints them as `path_taken`)
+static long long g_fused_paths[2] = {0, 0};
+extern "C" int gnnml3_fused_path_counts(long long* out2_host, int reset) {
+    out2_host[0] = g_fused_paths[0];
+    out2_host[1] = g_fused_paths[1];
+    if (reset) g_fused_paths[0] = g_fused_paths[1] = 0;
+    return GNNML3_OK;
+}
+namespace gnnml3 {
+void fused_path_count(int which) { ++g_fused_paths[which]; }
+}
+
+// 1 = use the tensor-memory kernel where the shape allows (default), 0 = always the round-1 kernel; returns the old value
+extern "C" int gnnml3_fused_set_ts(int enable) {
+    const int old = g_ts_runtime_enabled;
+    if (enable == 0 || enable == 1) g_ts_runtime_enabled = enable;
+    return old;
+}
+
+static inline int ts_kt_for(int K, int Kstride) {
+    if (K % 4 == 0 && Kstride % 4 == 0) return 4;
+    if (K % 2 == 0 && Kstride % 2 == 0) return 2;
+    return 0;
+}
+
+constexpr size_t TS_SMEM_MAX = 227 * 1024;
+
+static inline size_t ts_smem_bytes(int K, int Nc, int self_mode) {
+    const size_t wplane = 2 * (size_t)(Nc <= 32 ? 32 : 64) * 128;
+    return 1024 + 2 * (size_t)TS_WIN_ROWS * 128 + (size_t)(K + (self_mode != 0 ? 1 : 0)) * wplane + 256;
+}
+
+extern "C" int gnnml3_fused_ts_supported(int K, int Kstride, int F, int Nc, int Fs, int self_mode, int Ns) {
+    if (!g_ts_enabled || !g_ts_runtime_enabled) return 0;
+    if (ts_kt_for(K, Kstride) == 0 || K < 1 || K > 24) return 0;     // accumulation chain per tile kept short (TMEM adds truncate)
+    if (F < 1 || F > 32 || Nc < 1 || Nc > 64) return 0;
+    if (self_mode != 0 && (Fs < 1 || Fs > 32)) return 0;
+    if (self_mode == 1 && (Ns < 2 || Ns > 32 || Ns % 2 != 0 || Nc > 32)) return 0;
+    if (ts_smem_bytes(K, Nc, self_mode) > TS_SMEM_MAX) return 0;
+    return 1;
+}
+
+extern "C" size_t gnnml3_fused_ts_workspace_bytes(int K, int Nc, int self_mode) {
+    return align_up((size_t)(K + (self_mode != 0 ? 1 : 0)) * 2 * (Nc <= 32 ? 32 : 64) * 128, 256);
+}
+
+namespace gnnml3 {
+
+struct TSProfHook {
+    void (*begin)(cudaStream_t, const double*);
+    void (*end)(cudaStream_t);
+};
+TSProfHook g_ts_prof = {nullptr, nullptr};
+
+template <int KT, int BNH>
+static int ts_launch(const CUtensorMap& mW, const CUtensorMap& mX, TSParams& P, size_t smem, cudaStream_t st) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured))
+        GNNML3_CUDA(cudaFuncSetAttribute(k_fused_ts<KT, BNH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM_MAX));
+    const int grid = P.n_tiles < kNumSMs ? P.n_tiles : kNumSMs;
+    k_fused_ts<KT, BNH><<<grid, TS_THREADS, smem, st>>>(mW, mX, P);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+// X [N, F] (row stride ldx) -> 2-D tensor map with a [box_rows x 32 columns] box, 128B swizzle; columns >= F and rows >= N
+// are zero-filled by the TMA unit
+static int ts_make_xmap(CUtensorMap* map, const float* base, int64_t rows, int F, int64_t ld, int box_rows) {
+    PFN_encodeTiled enc = get_encoder();
+    if (!enc) return set_err(GNNML3_ERR_CUDA, "fused_agg_proj: cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(GNNML3_ERR_CUDA, "fused_agg_proj: cuTensorMapEncodeTiled(X) failed (%d)", (int)r);
+    return GNNML3_OK;
+}
+
+// called by gnnml3_fused_agg_proj (fused_layer.cu) after argument validation, when gnnml3_fused_ts_supported() holds
+int fused_ts_run(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea, int Kstride, int K, const float* X,
+                 int64_t ldx, int F, const float* S, int64_t lds, int Fs, int self_mode, const float* Bmain, int64_t ldb,
+                 const float* Bself, int64_t ldbs, int Ns, const float* bias, const float* bias_s, int64_t N, int Nc, float* out,
+                 int64_t ldo, float* aux, int64_t ldaux, int G, int epilogue, float* hout, int64_t ldh, const int32_t* tilewin,
+                 void* workspace, size_t workspace_bytes, unsigned long long* dbg, cudaStream_t st) {
+    if (workspace_bytes < gnnml3_fused_ts_workspace_bytes(K, Nc, self_mode))
+        return set_err(GNNML3_ERR_WORKSPACE, "fused_agg_proj: workspace too small");
+    const int BNH = Nc <= 32 ? 32 : 64;
+    const int KT = ts_kt_for(K, Kstride);
+    const int nkb_total = K + (self_mode != 0 ? 1 : 0);
+    float* planes = (float*)workspace;
+    {
+        const int total = nkb_total * 2 * BNH * 32;
+        const int blocks = cdiv(total, 256) > 592 ? 592 : cdiv(total, 256);
+        k_ts_prep_weights<<<blocks, 256, 0, st>>>(Bmain, ldb, K, F, Nc, BNH, Bself, ldbs, Fs, Ns, self_mode, planes);
+        GNNML3_LAUNCH_CHECK();
+    }
+    CUtensorMap mW, mX;
+    int rc;
+    if ((rc = make_map(&mW, planes, (int64_t)nkb_total * 2 * BNH, 32, 32, 2 * BNH))) return rc;
+    const int win_rows = N < TS_WIN_ROWS ? (int)N : TS_WIN_ROWS;
+    if ((rc = ts_make_xmap(&mX, X, N, F, ldx, win_rows))) return rc;
+    TSParams P;
+    P.rowptr = rowptr; P.col = col; P.eperm = eperm; P.ea = ea; P.Kstride = Kstride; P.K = K;
+    P.X = X; P.ldx = ldx; P.F = F; P.S = S; P.lds = lds; P.Fs = Fs; P.self_mode = self_mode;
+    P.N = N; P.n_tiles = cdiv(N, TS_ROWS); P.nkb_main = K; P.tilewin = reinterpret_cast<const int2*>(tilewin); P.win_rows = win_rows;
+    P.bias = bias; P.bias_s = bias_s; P.out = out; P.ldo = ldo; P.Nc = Nc; P.aux = aux; P.ldaux = ldaux; P.G = G; P.epi = epilogue;
+    P.hout = hout; P.ldh = ldh; P.dbg = dbg;
+    const size_t smem = ts_smem_bytes(K, Nc, self_mode);
+    if (BNH == 32) return KT == 4 ? ts_launch<4, 32>(mW, mX, P, smem, st) : ts_launch<2, 32>(mW, mX, P, smem, st);
+    return KT == 4 ? ts_launch<4, 64>(mW, mX, P, smem, st) : ts_launch<2, 64>(mW, mX, P, smem, st);
+}
+
+}  // namespace gnnml3

@@ -125,7 +125,7 @@ extern "C" size_t gnnml3_ml3layer_workspace_bytes(int64_t N, int64_t E, int K, i
     return layer_ws(N, E, K, Fi, Fo, G).total_bwd;
 }
 
-extern "C" int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col, int64_t N, int64_t E, const float* x, int64_t ldx,
+extern "C" int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col, const int32_t* win, int64_t N, int64_t E, const float* x, int64_t ldx,
                                        int Fi, const float* ea_s, int K, const float* w1, const float* w2, const float* w3,
                                        const float* w4, const float* wconv, const float* bconv, int Fo, const float* w11,
                                        const float* b11, const float* w12, const float* b12, int G, float* ea2, float* y,
@@ -151,11 +151,11 @@ extern "C" int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col
         GNNML3_LAUNCH_CHECK();
     }
     return gnnml3_fused_agg_proj(rowptr, col, nullptr, eaw, K, K, x, ldx, Fi, G > 0 ? x : nullptr, ldx, G > 0 ? Fi : 0, G > 0 ? 1 : 0, wconv,
-                                 Fo, wg, 2 * G, 2 * G, bconv, bg, N, Fo, y, ldy, aux, 2 * G, G, 1, nullptr, 0, ws + w.fused, w.wg - w.fused, stream);
+                                 Fo, wg, 2 * G, 2 * G, bconv, bg, N, Fo, y, ldy, aux, 2 * G, G, 1, nullptr, 0, win, ws + w.fused, w.wg - w.fused, stream);
 }
 
 extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* rowptrT, const int32_t* colT,
-                                        const int32_t* permT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
+                                        const int32_t* permT, const int32_t* winT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
                                         const float* ea_s, const float* ea2, int K, const float* w1, const float* w2, const float* w3,
                                         const float* w4, const float* wconv, int Fo, const float* w11, const float* w12, int G,
                                         const float* y, int64_t ldy, const float* aux, const float* gy, int64_t ldgy, int need_dx,
@@ -189,13 +189,13 @@ extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* co
         ldG = (int64_t)(K + (G > 0 ? 1 : 0)) * 32;
         if ((rc = gnnml3_fused_agg_proj(rowptrT, colT, permT, eaw, K, K, gpre, w.ldg, Fo, G > 0 ? gpre + Fo4 : nullptr, w.ldg, 2 * G,
                                         G > 0 ? 2 : 0, wT, Fi, G > 0 ? ws2 : nullptr, Fi, 0, nullptr, nullptr, N, Fi, dx, lddx, nullptr, 0, 0,
-                                        0, Gp, ldG, ws + w.fused, w.wg - w.fused, stream)))
+                                        0, Gp, ldG, winT, ws + w.fused, w.wg - w.fused, stream)))
             return rc;
     } else {
         if (need_dx) {
             if ((rc = gnnml3_fused_agg_proj(rowptrT, colT, permT, eaw, K, K, gpre, w.ldg, Fo, G > 0 ? gpre + Fo4 : nullptr, w.ldg, 2 * G,
                                             G > 0 ? 2 : 0, wT, Fi, G > 0 ? ws2 : nullptr, Fi, 0, nullptr, nullptr, N, Fi, dx, lddx, nullptr, 0,
-                                            0, 0, nullptr, 0, ws + w.fused, w.wg - w.fused, stream)))
+                                            0, 0, nullptr, 0, winT, ws + w.fused, w.wg - w.fused, stream)))
                 return rc;
         }
         pitch = Fo;

@@ -21,7 +21,7 @@ def set_range_check(flag):
 
 
 class GraphPlan(object):
-    __slots__ = ("N", "E", "rowptr", "col", "perm", "rowptrT", "colT", "permT", "device")
+    __slots__ = ("N", "E", "rowptr", "col", "perm", "rowptrT", "colT", "permT", "win", "winT", "device")
 
     def __init__(self, edge_index, num_nodes, check_range=True):
         d = ops.csr_build(edge_index, num_nodes, check_range=check_range)

@@ -85,7 +85,7 @@ class _SpectConvFn(torch.autograd.Function):
             x = ops.aligned_rows(x)
             out, _ = ops.fused_agg_proj(plan.rowptr, plan.col, None, ea_s, x, weight[:K].reshape(K * Fi, Fo), bias=bias,
                                         S=x if selfconn else None, self_mode=2 if selfconn else 0,
-                                        Bself=weight[K] if selfconn else None, epilogue=0)
+                                        Bself=weight[K] if selfconn else None, epilogue=0, win=plan.win)
         else:
             H = _aggregate(plan, ea_s, x, Kw)
             if selfconn:
@@ -121,7 +121,8 @@ class _SpectConvFn(torch.autograd.Function):
             dx, _ = ops.fused_agg_proj(plan.rowptrT, plan.colT, plan.permT, ea_s, gout,
                                        weight[:K].transpose(1, 2).reshape(K * Fo, Fi).contiguous(),
                                        S=gout if ctx.selfconn else None, self_mode=2 if ctx.selfconn else 0,
-                                       Bself=weight[K].t().contiguous() if ctx.selfconn else None, epilogue=0, hout=G)
+                                       Bself=weight[K].t().contiguous() if ctx.selfconn else None, epilogue=0, hout=G,
+                                       win=plan.winT)
             if side:
                 dcat = ops.gemm_tn(x, G, precision=prec)                                          # [Fi, Kw * Fp]
                 dw = dcat.view(Fi, Kw, Fp)[:, :, :Fo].permute(1, 0, 2).contiguous()
@@ -255,7 +256,7 @@ class _ML3LayerFn(torch.autograd.Function):
             bg = torch.cat([b11, b12]) if G > 0 else None
             y, aux = ops.fused_agg_proj(plan.rowptr, plan.col, None, ea2, xa, wconv.view(K * Fi, Fo), bias=bconv,
                                         S=xa if G > 0 else None, self_mode=1 if G > 0 else 0, Bself=wg, bias_s=bg, G=G,
-                                        epilogue=1)
+                                        epilogue=1, win=plan.win)
             ctx.save_for_backward(xa, ea_s, ea2 if fused_edge else None, y, aux, w1, w2, w3, w4, wconv, w11, w12)
             return y
         H = _aggregate(plan, ea2, x, K)
@@ -315,7 +316,8 @@ class _ML3LayerFn(torch.autograd.Function):
             dx, _ = ops.fused_agg_proj(plan.rowptrT, plan.colT, plan.permT, ea2, gpre[:, :Fo],
                                        wconv.transpose(1, 2).reshape(K * Fo, Fi).contiguous(),
                                        S=gpre[:, Fo4:Fo4 + 2 * G] if G > 0 else None, self_mode=2 if G > 0 else 0,
-                                       Bself=torch.cat([w11, w12], 0).contiguous() if G > 0 else None, epilogue=0)
+                                       Bself=torch.cat([w11, w12], 0).contiguous() if G > 0 else None, epilogue=0,
+                                       win=plan.winT)
         elif need[0]:
             blocks = [wconv.transpose(1, 2).reshape(K * Fo, Fi)]
             if G > 0:

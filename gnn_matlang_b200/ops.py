@@ -89,7 +89,31 @@ def csr_build(edge_index, num_nodes, check_range=True):
     _lib.check(rc, "gnnml3_csr_build")
     if check_range and int(flag.item()) != 0:
         raise RuntimeError("edge_index contains node ids outside [0, %d)" % N)
+    if E > 0:
+        # per-tile source windows of both CSRs (the fused layer kernel stages a tile's source rows in shared memory)
+        nt = (N + lib.gnnml3_tile_rows() - 1) // lib.gnnml3_tile_rows()
+        out["win"] = torch.empty(nt, 2, **i32)
+        out["winT"] = torch.empty(nt, 2, **i32)
+        with _on(dev):
+            _lib.check(lib.gnnml3_tile_windows(_lib.ptr(out["rowptr"]), _lib.ptr(out["col"]), N, _lib.ptr(out["win"]),
+                                               _lib.stream_ptr()), "gnnml3_tile_windows")
+            _lib.check(lib.gnnml3_tile_windows(_lib.ptr(out["rowptrT"]), _lib.ptr(out["colT"]), N, _lib.ptr(out["winT"]),
+                                               _lib.stream_ptr()), "gnnml3_tile_windows")
+    else:
+        out["win"] = out["winT"] = None
     return out
+
+
+def tile_windows(rowptr, col):
+    """[n_tiles, 2] int32 {first, last + 1} source row of each tile of the CSR (gnnml3_tile_windows)."""
+    lib = _lib.load()
+    N = rowptr.numel() - 1
+    nt = (N + lib.gnnml3_tile_rows() - 1) // lib.gnnml3_tile_rows()
+    win = torch.empty(nt, 2, dtype=torch.int32, device=rowptr.device)
+    with _on(rowptr.device):
+        _lib.check(lib.gnnml3_tile_windows(_lib.ptr(rowptr), _lib.ptr(col), N, _lib.ptr(win), _lib.stream_ptr()),
+                   "gnnml3_tile_windows")
+    return win
 
 
 def gather_rows(src, perm):
@@ -318,7 +342,7 @@ def fused_supported(K, Kstride, F, Nc, Fs=0, self_mode=0, Ns=0):
 
 
 def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mode=0, Bself=None, bias_s=None, G=0,
-                   epilogue=0, hout=None):
+                   epilogue=0, hout=None, win=None):
     """Fused aggregate + project (gnnml3_fused_agg_proj).  x [*, F] and S [N, Fs] must satisfy ``aligned_rows``.
     epilogue 0 -> out [N, Nc];  epilogue 1 -> (y [N, Nc + G], aux [N, 2G]) = the ML3Layer node branch."""
     lib = _lib.load()
@@ -358,7 +382,7 @@ def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mod
             _lib.ptr(S) if self_mode else None, _ld(S) if self_mode else 0, Fs, self_mode, _lib.ptr(Bmain), _ld(Bmain),
             _lib.ptr(Bself) if self_mode else None, _ld(Bself) if self_mode else 0, Ns, _lib.ptr(bias), _lib.ptr(bias_s),
             N, Nc, _lib.ptr(out), ldo, _lib.ptr(aux), 2 * G, G, epilogue, _lib.ptr(hout), _ld(hout) if hout is not None else 0,
-            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            _lib.ptr(win), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
             "gnnml3_fused_agg_proj")
     return out, aux
 
@@ -379,6 +403,14 @@ def ml3_act_bwd_y(y, aux, gy, Fo, G):
                                             _lib.ptr(gpre), ldg, _lib.ptr(csum), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                    "gnnml3_ml3_act_bwd_y")
     return gpre, csum
+
+
+def fused_path_counts(reset=False):
+    """(launches of the tensor-memory fused kernel, launches of the shared-memory-plane kernel) since the last reset."""
+    import ctypes
+    buf = (ctypes.c_longlong * 2)()
+    _lib.load().gnnml3_fused_path_counts(buf, int(bool(reset)))
+    return int(buf[0]), int(buf[1])
 
 
 def fused_side_output_ok():
@@ -431,7 +463,7 @@ def ml3layer_forward(plan, x, ea_s, ws4, wconv, bconv, gates):
     w = ws4 if ws4 is not None else (None,) * 4
     g = gates if gates is not None else (None,) * 4
     with _on(dev):
-        _lib.check(lib.gnnml3_ml3layer_forward(p(plan.rowptr), p(plan.col), N, E, p(x), _ld(x), Fi, p(ea_s), K, p(w[0]), p(w[1]), p(w[2]),
+        _lib.check(lib.gnnml3_ml3layer_forward(p(plan.rowptr), p(plan.col), p(plan.win), N, E, p(x), _ld(x), Fi, p(ea_s), K, p(w[0]), p(w[1]), p(w[2]),
                                                p(w[3]), p(wconv), p(bconv), Fo, p(g[0]), p(g[1]), p(g[2]), p(g[3]), G, p(ea2), p(y), ldy,
                                                p(aux), p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_forward")
     return y[:, :W], aux, ea2
@@ -461,7 +493,7 @@ def ml3layer_backward(plan, x, ea_s, ea2, ws4, wconv, gates_w, y, aux, gy, need_
     gw = gates_w if gates_w is not None else (None, None)
     with _on(dev):
         _lib.check(lib.gnnml3_ml3layer_backward(
-            p(plan.rowptr), p(plan.col), p(plan.rowptrT), p(plan.colT), p(plan.permT), N, E, p(x), _ld(x), Fi, p(ea_s), p(ea2), K,
+            p(plan.rowptr), p(plan.col), p(plan.rowptrT), p(plan.colT), p(plan.permT), p(plan.winT), N, E, p(x), _ld(x), Fi, p(ea_s), p(ea2), K,
             p(w[0]), p(w[1]), p(w[2]), p(w[3]), p(wconv), Fo, p(gw[0]), p(gw[1]), G, p(y), _ld(y), p(aux), p(gy), _ld(gy),
             int(need_dx), int(need_dea), p(dx), lddx, p(dea), p(dws[0]), p(dws[1]), p(dws[2]), p(dws[3]), p(dwc), p(dbias), p(dw11),
             p(dw12), p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_backward")

@@ -168,7 +168,21 @@ GNNML3_API int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
                           int Fs, int self_mode, const float* Bmain, int64_t ldb, const float* Bself,
                           int64_t ldbs, int Ns, const float* bias, const float* bias_s, int64_t N, int Nc,
                           float* out, int64_t ldo, float* aux, int64_t ldaux, int G, int epilogue,
-                          float* hout, int64_t ldh, void* workspace, size_t workspace_bytes, void* stream);
+                          float* hout, int64_t ldh, const int32_t* tilewin, void* workspace, size_t workspace_bytes,
+                          void* stream);
+/* Second generation of the same kernel (fused_layer_ts.cu), taken automatically when the shape allows (F <= 32, even K):
+ * the aggregate is handed to the tensor core through TENSOR MEMORY (tcgen05.st + A-in-TMEM tcgen05.mma) and the gathered
+ * rows are staged in shared memory by one TMA box load per tile.  `tilewin` (nullable) = gnnml3_tile_windows() of the SAME
+ * CSR: [ceil(N / gnnml3_tile_rows())][2] int32 {first, last + 1} source row of each tile's slots; tiles whose window has
+ * at most 256 rows read their sources from shared memory, the others (and tilewin == NULL) gather from global memory.
+ * gnnml3_fused_set_ts(0) forces the first-generation kernel; gnnml3_fused_path_counts reports which kernel ran
+ * ([0] tensor-memory, [1] shared-memory planes) since the last reset. */
+GNNML3_API int gnnml3_tile_rows(void);
+GNNML3_API int gnnml3_tile_windows(const int32_t* rowptr, const int32_t* col, int64_t N, int32_t* win, void* stream);
+GNNML3_API int gnnml3_fused_ts_supported(int K, int Kstride, int F, int Nc, int Fs, int self_mode, int Ns);
+GNNML3_API size_t gnnml3_fused_ts_workspace_bytes(int K, int Nc, int self_mode);
+GNNML3_API int gnnml3_fused_set_ts(int enable);
+GNNML3_API int gnnml3_fused_path_counts(long long* out2_host, int reset);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused edge-feature gradient (fused_sddmm.cu):  dea[p, k] = < X[col[p], :], GC[t, :] W[k]^T >  for every CSR slot p of
@@ -194,16 +208,17 @@ GNNML3_API int gnnml3_fused_sddmm(const int32_t* rowptr, const int32_t* col, con
  *   backward: gy [N, ldgy]; outputs dx [N, lddx] (if need_dx), dea [E,K] (if need_dea), dw1..dw4, dwconv [K,Fi,Fo],
  *             dbias [Fo + 2G] = (d bconv | d b11 | d b12), dw11/dw12 [G,Fi].
  * x rows must be 16-byte aligned (ldx % 4 == 0).  gnnml3_ml3layer_supported tells whether a shape is covered.
+ * win / winT (nullable) = gnnml3_tile_windows of the dst-sorted / transposed CSR (see gnnml3_fused_agg_proj).
  * --------------------------------------------------------------------------------------------------- */
 GNNML3_API int gnnml3_ml3layer_supported(int K, int Fi, int Fo, int G, int learnedge);
 GNNML3_API size_t gnnml3_ml3layer_workspace_bytes(int64_t N, int64_t E, int K, int Fi, int Fo, int G);
-GNNML3_API int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col, int64_t N, int64_t E, const float* x, int64_t ldx,
+GNNML3_API int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col, const int32_t* win, int64_t N, int64_t E, const float* x, int64_t ldx,
                             int Fi, const float* ea_s, int K, const float* w1, const float* w2, const float* w3,
                             const float* w4, const float* wconv, const float* bconv, int Fo, const float* w11,
                             const float* b11, const float* w12, const float* b12, int G, float* ea2, float* y,
                             int64_t ldy, float* aux, void* workspace, size_t workspace_bytes, void* stream);
 GNNML3_API int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* rowptrT, const int32_t* colT,
-                             const int32_t* permT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
+                             const int32_t* permT, const int32_t* winT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
                              const float* ea_s, const float* ea2, int K, const float* w1, const float* w2, const float* w3,
                              const float* w4, const float* wconv, int Fo, const float* w11, const float* w12, int G,
                              const float* y, int64_t ldy, const float* aux, const float* gy, int64_t ldgy, int need_dx,

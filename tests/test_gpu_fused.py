@@ -44,14 +44,34 @@ CASES = [  # N, deg, K, F, Nc, G
 ]
 
 
-@pytest.fixture(params=[0, 1], ids=["gather-global", "prefetch-slots"])
+@pytest.fixture(params=["ts-window", "ts-global", "planes-gather", "planes-slots"])
 def fused_mode(request):
-    """Both aggregator modes of the fused kernel (gnnml3_fused_set_mode)."""
+    """Every variant of the fused kernel: the tensor-memory generation (fused_layer_ts.cu) with the tile's source rows staged
+    in shared memory (tile windows given) or gathered from global memory, and the shared-memory-plane generation
+    (fused_layer.cu) in both aggregator modes (gnnml3_fused_set_ts / gnnml3_fused_set_mode)."""
     from gnn_matlang_b200 import _lib
     lib = _lib.load()
-    old = lib.gnnml3_fused_set_mode(request.param)
+    ts = request.param.startswith("ts")
+    old_ts = lib.gnnml3_fused_set_ts(1 if ts else 0)
+    old = lib.gnnml3_fused_set_mode(1 if request.param == "planes-slots" else 0)
     yield request.param
     lib.gnnml3_fused_set_mode(old)
+    lib.gnnml3_fused_set_ts(old_ts)
+
+
+def _win(mode, rowptr, col):
+    from gnn_matlang_b200 import ops
+    return ops.tile_windows(rowptr, col) if mode == "ts-window" else None
+
+
+def _check_path(mode, K, F, before):
+    """The variant under test is the one that ran (no silent fall-through to the other generation)."""
+    from gnn_matlang_b200 import ops
+    ts, planes = ops.fused_path_counts()
+    if mode.startswith("ts") and F <= 32 and K % 2 == 0:
+        assert ts > before[0] and planes == before[1], "tensor-memory kernel did not run"
+    else:
+        assert planes > before[1] and ts == before[0], "shared-memory-plane kernel did not run"
 
 
 @pytest.mark.parametrize("N,deg,K,F,Nc,G", CASES)
@@ -72,6 +92,8 @@ def test_fused_forward_ml3(N, deg, K, F, Nc, G, fused_mode):
     i32 = lambda a: torch.from_numpy(a.astype(np.int32)).to(d)
     xa = ops.aligned_rows(x.to(d))
     ref = _ref_main(x, ei, ea, W, bias)
+    win = _win(fused_mode, i32(csr["rowptr"]), i32(csr["col"]))
+    before = ops.fused_path_counts()
     if G > 0 and F <= 32:
         w11 = torch.randn(G, F, generator=g) / np.sqrt(F)
         w12 = torch.randn(G, F, generator=g) / np.sqrt(F)
@@ -79,7 +101,7 @@ def test_fused_forward_ml3(N, deg, K, F, Nc, G, fused_mode):
         wg = torch.cat([w11.t(), w12.t()], 1).contiguous().to(d)
         y, aux = ops.fused_agg_proj(i32(csr["rowptr"]), i32(csr["col"]), None, ea_s.to(d), xa, W.view(K * F, Nc).to(d),
                                     bias=bias.to(d), S=xa, self_mode=1, Bself=wg, bias_s=torch.cat([b11, b12]).to(d), G=G,
-                                    epilogue=1)
+                                    epilogue=1, win=win)
         t1 = torch.tanh(x.double() @ w11.double().t() + b11.double())
         t2 = torch.tanh(x.double() @ w12.double().t() + b12.double())
         assert_close(y[:, :Nc], torch.relu(ref), name="relu(conv)")
@@ -87,9 +109,10 @@ def test_fused_forward_ml3(N, deg, K, F, Nc, G, fused_mode):
         assert_close(aux, torch.cat([t1, t2], 1), name="aux")
     else:
         out, aux = ops.fused_agg_proj(i32(csr["rowptr"]), i32(csr["col"]), None, ea_s.to(d), xa, W.view(K * F, Nc).to(d),
-                                      bias=bias.to(d), epilogue=0)
+                                      bias=bias.to(d), epilogue=0, win=win)
         assert aux is None
         assert_close(out, ref, name="conv")
+    _check_path(fused_mode, K, F, before)
 
 
 @pytest.mark.parametrize("N,deg,K,F,Nc,Fs", [(3000, 6, 8, 30, 32, 4), (2000, 5, 6, 32, 2, 32), (1200, 4, 10, 64, 64, 0),
@@ -120,7 +143,8 @@ def test_fused_transposed_with_self_block(N, deg, K, F, Nc, Fs, fused_mode):
     bufd = buf.to(d)
     out, _ = ops.fused_agg_proj(i32(csr["rowptrT"]), i32(csr["colT"]), i32(csr["permT"]), ea_s.to(d), bufd[:, :F],
                                 W.view(K * F, Nc).to(d), S=bufd[:, F4:F4 + Fs] if Fs else None, self_mode=2 if Fs else 0,
-                                Bself=Bs.to(d) if Fs else None, epilogue=0)
+                                Bself=Bs.to(d) if Fs else None, epilogue=0,
+                                win=_win(fused_mode, i32(csr["rowptrT"]), i32(csr["colT"])))
     assert_close(out, ref, name="dx form")
 
 
@@ -134,10 +158,67 @@ def test_fused_large_batch_matches_two_kernel_path(fused_mode):
     x = torch.randn(N, F, generator=g).to(d)
     ea_s = torch.randn(ei.size(1), K, generator=g).to(d)
     W = (torch.randn(K * F, Nc, generator=g) / 16).to(d)
-    out, _ = ops.fused_agg_proj(plan["rowptr"], plan["col"], None, ea_s, x, W, epilogue=0)
+    out, _ = ops.fused_agg_proj(plan["rowptr"], plan["col"], None, ea_s, x, W, epilogue=0,
+                                win=plan["win"] if fused_mode == "ts-window" else None)
     H = ops.spmm_k(plan["rowptr"], plan["col"], None, ea_s, x)
     ref = ops.gemm_nn(H, W)
     assert_close(out, ref, rtol=2e-6, name="fused vs two-kernel")
+
+
+def test_tile_windows_are_exact():
+    """gnnml3_tile_windows: {min, max + 1} source row over each 128-row tile's CSR slots ({0, 0} for an empty tile) -- integer
+    work, bit-exact against numpy."""
+    from gnn_matlang_b200 import _lib, ops
+    rows = _lib.load().gnnml3_tile_rows()
+    for N, deg, blk in [(1000, 5, 40), (4097, 3, 700), (130, 1, 13)]:
+        ei, _ = _graph(N, deg, N, blk=blk)
+        ei = ei[:, ei[1] >= 300] if N == 1000 else ei          # rows 0..299 without any slot: tiles 0 and 1 are empty
+        csr = np_csr(ei.numpy(), N)
+        d = dev()
+        win = ops.tile_windows(torch.from_numpy(csr["rowptr"].astype(np.int32)).to(d),
+                               torch.from_numpy(csr["col"].astype(np.int32)).to(d)).cpu().numpy()
+        nt = (N + rows - 1) // rows
+        assert win.shape == (nt, 2)
+        for t in range(nt):
+            e0, e1 = csr["rowptr"][t * rows], csr["rowptr"][min((t + 1) * rows, N)]
+            c = csr["col"][e0:e1]
+            exp = (0, 0) if e1 == e0 else (int(c.min()), int(c.max()) + 1)
+            assert tuple(win[t]) == exp, (N, t, tuple(win[t]), exp)
+
+
+def test_fused_ts_mixed_windows_and_side_output():
+    """Tensor-memory kernel on a graph whose first half has local edges (tiles staged in shared memory) and whose second half
+    has long-range edges (windows wider than the TMA box: those tiles gather from global memory) -- one launch, both
+    aggregator paths; plus the aggregate side output `hout` the backward's weight gradient consumes."""
+    from gnn_matlang_b200 import ops
+    N, deg, K, F, Nc = 6000, 5, 8, 30, 32
+    g = torch.Generator().manual_seed(99)
+    E = N * deg
+    src = torch.randint(0, N, (E,), generator=g)
+    near = ((src // 40) * 40 + torch.randint(0, 40, (E,), generator=g)).clamp(max=N - 1)
+    far = torch.randint(N // 2, N, (E,), generator=g)
+    dst = torch.where(src < N // 2, near, far)
+    ei = torch.stack([src, dst])
+    x = torch.randn(N, F, generator=g)
+    ea = torch.randn(E, K, generator=g)
+    W = torch.randn(K, F, Nc, generator=g) / np.sqrt(K * F)
+    d = dev()
+    plan = ops.csr_build(ei.to(d), N)
+    win = plan["win"].cpu().numpy()
+    width = win[:, 1] - win[:, 0]
+    assert (width <= 256).any() and (width > 256).any(), "the case must contain staged and unstaged tiles"
+    ea_s = ea.to(d)[plan["perm"].long()].contiguous()
+    xa = ops.aligned_rows(x.to(d))
+    hout = torch.full((N, K * 32), float("nan"), device=d)
+    before = ops.fused_path_counts()
+    out, _ = ops.fused_agg_proj(plan["rowptr"], plan["col"], None, ea_s, xa, W.view(K * F, Nc).to(d), epilogue=0, hout=hout,
+                                win=plan["win"])
+    assert ops.fused_path_counts()[0] == before[0] + 1
+    assert_close(out, _ref_main(x, ei, ea, W, None), name="conv (mixed windows)")
+    H = torch.zeros(N, K, 32, dtype=torch.float64)
+    for k in range(K):
+        H[:, k, :F] = torch.zeros(N, F, dtype=torch.float64).index_add_(0, ei[1], ea[:, k:k + 1].double() * x.double()[ei[0]])
+    assert_close(hout, H.view(N, K * 32), name="aggregate side output")
 
 
 @pytest.mark.parametrize("N,deg,K,Fi,Fo", [(3000, 6, 8, 32, 30), (3001, 5, 8, 25, 30), (1000, 7, 6, 2, 32), (60, 3, 2, 8, 8),
