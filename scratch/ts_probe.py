@@ -42,6 +42,8 @@ def counters(tag):
         return
     print("   [%s] per launch, summed over CTAs: agg gather %.3g slot-wait %.3g window-wait %.3g total %.3g | mma wait_full %.3g wait_tempty %.3g total %.3g | epi wait %.3g total %.3g"
           % (tag, c[0], c[1], c[8], c[2], c[3], c[4], c[5], c[6], c[7]))
+    print("   per aggregator warp and tile (cycles): gather %.0f (inner loop %.0f for %.1f steps = %.0f per step), dump+slot waits %.0f, stage wait %.0f, total %.0f"
+          % (c[0] / 1184 / 10, c[10] / 1184 / 10, c[13] / 1184 / 10, c[10] / max(c[13], 1), c[9] / 1184 / 10, c[8] / 1184 / 10, c[2] / 1184 / 10))
     print("   fractions: agg gather %.2f slot-wait %.2f window-wait %.2f | mma wait_full %.2f wait_tempty %.2f busy %.2f | epi wait %.2f ; MMA loop cycles per CTA %.3g"
           % (c[0] / c[2], c[1] / c[2], c[8] / c[2], c[3] / c[5], c[4] / c[5], 1 - (c[3] + c[4]) / c[5], c[6] / max(c[7], 1), c[5] / 148))
 
