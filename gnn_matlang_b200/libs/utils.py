@@ -39,10 +39,16 @@ class SpectralDesign(object):
         return self.nfreq + 1 + (1 if self.addadj else 0)
 
     # ------------------------------------------------------------------------------------------ batched
-    def design_batch(self, edge_index, edge_ptr, node_ptr, device=None, global_ids=False):
+    def design_batch(self, edge_index, edge_ptr, node_ptr, device=None, global_ids=False, max_entries=None):
         """edge_index [2, Etot] int64 with LOCAL node ids, edge_ptr / node_ptr [B+1] (any int dtype, any device).
         Returns a dict of device tensors: edge_index2 [2, E2], edge_attr2 [E2, K], e2_ptr [B+1] (int64),
-        lmax [B], degree [Ntot]."""
+        lmax [B], degree [Ntot].
+
+        The number of mask entries E2 is data dependent: by default it is read back from the device (one host
+        synchronisation per call).  With ``max_entries`` (an upper bound, e.g. ``sum(n_b ** 2)``) nothing is read back:
+        the outputs have ``max_entries`` columns / rows, the tail beyond ``e2_ptr[-1]`` holds entries (0, 0) with all-zero
+        supports -- exactly neutral for SpectConv / ML3Layer (they add 0 to node 0 and receive zero gradients) -- so the
+        call is CUDA-graph capturable and the downstream CSR build needs no size from the device."""
         lib = _lib.load()
         if device is None:
             device = edge_index.device if edge_index.is_cuda else torch.device("cuda", torch.cuda.current_device())
@@ -63,9 +69,14 @@ class SpectralDesign(object):
                                                  max(nmax, 1), _lib.ptr(counts), st), "gnnml3_spectral_count")
             e2_ptr = torch.zeros(B + 1, dtype=torch.int64, device=device)
             torch.cumsum(counts, 0, out=e2_ptr[1:])
-            E2 = int(e2_ptr[-1].item()) if B > 0 else 0
-            ei2 = torch.empty(2, E2, dtype=torch.int64, device=device)
-            ea2 = torch.empty(E2, K, dtype=torch.float32, device=device)
+            if max_entries is not None:
+                E2 = int(max_entries)
+                ei2 = torch.zeros(2, E2, dtype=torch.int64, device=device)
+                ea2 = torch.zeros(E2, K, dtype=torch.float32, device=device)
+            else:
+                E2 = int(e2_ptr[-1].item()) if B > 0 else 0
+                ei2 = torch.empty(2, E2, dtype=torch.int64, device=device)
+                ea2 = torch.empty(E2, K, dtype=torch.float32, device=device)
             lmax = torch.zeros(B, dtype=torch.float32, device=device)
             deg = torch.zeros(Ntot, dtype=torch.float32, device=device)
             _lib.check(lib.gnnml3_spectral_design(

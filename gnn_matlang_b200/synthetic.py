@@ -112,7 +112,7 @@ class GraphPool(object):
         self.K = K or defaults[0]
         self.F = nfeat or defaults[1]
         self.recfield = defaults[2] if recfield is None else recfield
-        ns, xs, eis, eas, ys = [], [], [], [], []
+        ns, xs, eis, eis1, ys = [], [], [], [], []
         for _ in range(count):
             if kind == "zinc":
                 n, ei, x = zinc_graph(rng)
@@ -124,6 +124,7 @@ class GraphPool(object):
             ns.append(n)
             xs.append(x)
             eis.append(ei2)
+            eis1.append(ei)
             ys.append(rng.standard_normal())
         self.n = np.array(ns, dtype=np.int64)
         self.e = np.array([e.shape[1] for e in eis], dtype=np.int64)
@@ -131,6 +132,9 @@ class GraphPool(object):
         self.edge_off = np.concatenate([[0], np.cumsum(self.e)])
         self.x = np.concatenate(xs, 0)
         self.ei2 = np.concatenate(eis, 1)
+        self.ei1 = np.concatenate(eis1, 1)                  # the graphs' own edge lists (local ids): SpectralDesign's input
+        self.e1 = np.array([e.shape[1] for e in eis1], dtype=np.int64)
+        self.edge_off1 = np.concatenate([[0], np.cumsum(self.e1)])
         self.y = np.array(ys, dtype=np.float32)
         # edge features: N(0,1) placeholders unless real supports are attached with set_supports()
         self.ea2 = rng.standard_normal((self.ei2.shape[1], self.K)).astype(np.float32)
@@ -140,6 +144,32 @@ class GraphPool(object):
         assert ea2.shape == self.ea2.shape
         self.ea2 = np.ascontiguousarray(ea2, dtype=np.float32)
         self.supports = "spectral_design"
+
+    # SpectralDesign configuration of the reference script each pool kind mimics
+    SPECTRAL_CONFIGS = {
+        "zinc": dict(recfield=2, dv=2, nfreq=7),                                       # Zinc12k.py:12  -> K = 8
+        "counting": dict(recfield=1, dv=1, nfreq=10, laplacien=False, addadj=True),    # counting.py:16 -> K = 12
+        "sweep": dict(recfield=1, dv=2, nfreq=9),                                      # K = 10
+    }
+
+    def attach_spectral_supports(self, device):
+        """Replace the N(0,1) placeholder edge features by the real supports: gnn_matlang_b200's SpectralDesign (one launch
+        over the whole pool) with the reference script's settings.  The designed ``edge_index2`` must equal the pool's mask
+        coordinates bit for bit (same row-major order) -- checked."""
+        import torch
+        from .libs.utils import SpectralDesign
+        cfg = dict(self.SPECTRAL_CONFIGS[self.kind])
+        cfg["recfield"] = self.recfield
+        sd = SpectralDesign(**cfg)
+        if sd.num_supports != self.K:
+            raise RuntimeError("pool has K=%d, SpectralDesign config gives %d supports" % (self.K, sd.num_supports))
+        out = sd.design_batch(torch.from_numpy(self.ei1), torch.from_numpy(self.edge_off1), torch.from_numpy(self.node_off),
+                              device=device)
+        ei2 = out["edge_index2"].cpu().numpy()
+        if ei2.shape != self.ei2.shape or not np.array_equal(ei2, self.ei2):
+            raise RuntimeError("SpectralDesign mask coordinates differ from the pool's")
+        self.set_supports(out["edge_attr2"].cpu().numpy())
+        return self
 
     def draw(self, rng, B):
         idx = rng.integers(0, len(self.n), B)
@@ -159,3 +189,101 @@ class GraphPool(object):
         batch = torch.from_numpy(np.repeat(np.arange(len(idx), dtype=np.int64), n))
         return Batch(x=x, edge_index2=ei, edge_attr2=ea, batch=batch, num_graphs=len(idx),
                      graph_ptr=torch.from_numpy(goff.astype(np.int32)), y=torch.from_numpy(self.y[idx]).reshape(-1, 1))
+
+
+class ExpPool(object):
+    """Pool of REAL EXP graphs (the first 200 records of the reference's ``dataset/EXP/raw/GRAPHSAT.pkl``, committed as
+    ``tests/golden/exp_first200.npz`` by the golden-fixture script): BASELINE.json configs[2].  Unlike ``GraphPool`` the records
+    carry no supports: a batch is the raw graphs (node type ``x [n,1]``, local ``edge_index``) and the supports are rebuilt on
+    the GPU for every batch (``design_and_collate``), as the config asks."""
+
+    kind = "exp"
+    K = 6                      # exp_classify.py:16: SpectralDesign(recfield=1, dv=2, nfreq=5, adddegree=True) -> nfreq + 1 supports
+    F = 2                      # node type + degree column (adddegree)
+    supports = "spectral_design (rebuilt on the GPU every step)"
+
+    def __init__(self, path=None):
+        import os
+        if path is None:
+            path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "exp_first200.npz")
+        z = np.load(path)
+        self.n = z["n"].astype(np.int64)
+        self.e1 = z["ne"].astype(np.int64)
+        self.node_off = np.concatenate([[0], np.cumsum(self.n)])
+        self.edge_off1 = np.concatenate([[0], np.cumsum(self.e1)])
+        self.x = z["x"].astype(np.float32).reshape(-1, 1)
+        self.ei1 = z["edge_index"].astype(np.int64)
+        self.y = z["y"].astype(np.float32)
+
+    def draw_raw(self, rng, B):
+        """Host batch of B raw graphs: dict of torch tensors (x [N,1], edge_index [2,Etot] LOCAL ids, edge_ptr, node_ptr, y)."""
+        idx = rng.integers(0, len(self.n), B)
+        n, e = self.n[idx], self.e1[idx]
+        goff = np.concatenate([[0], np.cumsum(n)])
+        eoff = np.concatenate([[0], np.cumsum(e)])
+        nsel = np.repeat(self.node_off[idx] - goff[:-1], n) + np.arange(goff[-1])
+        esel = np.repeat(self.edge_off1[idx] - eoff[:-1], e) + np.arange(eoff[-1])
+        return dict(x=torch.from_numpy(self.x[nsel]), edge_index=torch.from_numpy(self.ei1[:, esel]),
+                    edge_ptr=torch.from_numpy(eoff.astype(np.int32)), node_ptr=torch.from_numpy(goff.astype(np.int32)),
+                    y=torch.from_numpy(self.y[idx]).reshape(-1, 1), num_graphs=int(B))
+
+
+def design_and_collate(raw, sd, device):
+    """Raw graphs (``ExpPool.draw_raw``, host or device tensors) -> device ``Batch`` with the supports designed on the GPU:
+    one ``SpectralDesign.design_batch(global_ids=True)`` launch emits the batched ``edge_index2`` / ``edge_attr2`` directly
+    (PyG's collation of ``edge_index2`` is the per-graph node offset the kernel adds), ``x`` gets the degree column
+    (``adddegree``) and ``batch`` / ``graph_ptr`` come from ``node_ptr``."""
+    node_ptr = raw["node_ptr"]
+    out = sd.design_batch(raw["edge_index"], raw["edge_ptr"], node_ptr, device=device, global_ids=True)
+    x = raw["x"].to(device, non_blocking=True)
+    if sd.adddegree:
+        x = torch.cat([x, out["degree"].unsqueeze(-1)], 1)
+    gp = node_ptr.to(device=device, dtype=torch.int32)
+    B = node_ptr.numel() - 1
+    batch = torch.repeat_interleave(torch.arange(B, device=device), (gp[1:] - gp[:-1]).long(), output_size=int(x.size(0)))
+    b = Batch(x=x, edge_index2=out["edge_index2"], edge_attr2=out["edge_attr2"], batch=batch, num_graphs=B, graph_ptr=gp,
+              y=raw["y"].to(device, non_blocking=True))
+    b.batch._gnnml3_ptr = (b.batch._version, gp)
+    return b
+
+
+class DeviceDataset(object):
+    """A ``GraphPool`` resident in HBM + collation ON THE DEVICE: the reference keeps its
+    ``InMemoryDataset`` in host memory, collates every batch on the host and copies all attributes host -> device each step
+    (Zinc12k.py:20-22, :360).  Here the per-graph records (features, graph-local support coordinates, supports, labels) are
+    uploaded once; a step's only host -> device traffic is the list of graph ids, and ``collate`` builds the reference's batch
+    attributes with a handful of index kernels -- bit-exact with ``GraphPool.collate`` / ``batch.collate`` (tested)."""
+
+    def __init__(self, pool, device):
+        self.device = device
+        self.n_h, self.e_h = pool.n, pool.e                      # host copies: batch sizes are known without a device round trip
+        t = lambda a, dt=None: torch.as_tensor(a if dt is None else a.astype(dt)).to(device)
+        self.n, self.e = t(pool.n), t(pool.e)
+        self.node_off, self.edge_off = t(pool.node_off), t(pool.edge_off)
+        self.x = t(pool.x)
+        self.el = t(pool.ei2)                                    # support coordinates, node ids local to their graph
+        self.ea = t(pool.ea2)
+        self.y = t(pool.y)
+
+    def collate(self, idx_host):
+        """``idx_host``: int64/int32 numpy array or pinned CPU tensor of graph ids -> device ``Batch``."""
+        idx_np = idx_host.numpy() if isinstance(idx_host, torch.Tensor) else np.asarray(idx_host)
+        N, E = int(self.n_h[idx_np].sum()), int(self.e_h[idx_np].sum())
+        idx = (idx_host if isinstance(idx_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(idx_np))).to(
+            self.device, non_blocking=True).long()
+        dev = self.device
+        B = idx.numel()
+        n, e = self.n[idx], self.e[idx]
+        gp = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(n, 0, out=gp[1:])
+        ep = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(e, 0, out=ep[1:])
+        nsel = torch.repeat_interleave(self.node_off[idx] - gp[:-1], n, output_size=N) + torch.arange(N, device=dev)
+        esel = torch.repeat_interleave(self.edge_off[idx] - ep[:-1], e, output_size=E) + torch.arange(E, device=dev)
+        ei = self.el[:, esel] + torch.repeat_interleave(gp[:-1], e, output_size=E).unsqueeze(0)
+        batch = torch.repeat_interleave(torch.arange(B, device=dev), n, output_size=N)
+        gp32 = gp.to(torch.int32)
+        out = Batch(x=self.x[nsel], edge_index2=ei, edge_attr2=self.ea[esel], batch=batch, num_graphs=B, graph_ptr=gp32,
+                    y=self.y[idx].reshape(-1, 1))
+        out.batch._gnnml3_ptr = (out.batch._version, gp32)
+        return out

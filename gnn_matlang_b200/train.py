@@ -55,16 +55,42 @@ class Trainer(object):
 
 
 class HostFeeder(object):
-    """Streams pinned host batches to the device one step ahead of the compute stream (H2D overlaps compute)."""
+    """Streams pinned host batches to the device one step ahead of the compute stream (H2D overlaps compute).
 
-    def __init__(self, device):
+    Host ``Batch`` objects are converted ONCE (first time they are seen) to the compact wire format (``batch.CompactBatch``:
+    int32 per-graph sizes instead of the int64 batch vector, graph-local uint8 edge ids instead of int64 global ids, one-hot
+    ``x`` as uint8 class codes); every step copies the compact tensors host -> device on the copy stream and the reference's
+    attributes are rebuilt on the device (``expand``) on the compute stream."""
+
+    format_note = ("compact wire format: n/e int32 per graph, graph-local uint8 edge ids, one-hot x as uint8 class codes, FP32 "
+                   "supports; edge_index2 (int64, global), batch and x are rebuilt on the device")
+
+    def __init__(self, device, onehot_widths=None):
         self.device = device
         self.copy_stream = torch.cuda.Stream(device=device)
+        self.onehot_widths = onehot_widths
         self._next = None
+        self._compact = {}
+
+    def compact(self, host_batch):
+        from .batch import CompactBatch
+        key = id(host_batch)
+        cb = self._compact.get(key)
+        if cb is None:
+            if isinstance(host_batch, CompactBatch):
+                cb = host_batch
+            else:
+                cb = CompactBatch.from_batch(host_batch, self.onehot_widths).pin_memory()
+            self._compact[key] = cb
+        return cb
+
+    def bytes_per_batch(self, host_batch):
+        return self.compact(host_batch).nbytes()
 
     def prefetch(self, host_batch):
+        cb = self.compact(host_batch)
         with torch.cuda.stream(self.copy_stream):
-            b = host_batch.to(self.device, non_blocking=True)
+            b = cb.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(self.copy_stream)
         self._next = (b, ev)
@@ -72,8 +98,7 @@ class HostFeeder(object):
     def get(self):
         b, ev = self._next
         torch.cuda.current_stream().wait_event(ev)
-        for v in b.__dict__.values():
-            if isinstance(v, torch.Tensor):
-                v.record_stream(torch.cuda.current_stream())
+        for v in b._tensors().values():
+            v.record_stream(torch.cuda.current_stream())
         self._next = None
-        return b
+        return b.expand()

@@ -221,3 +221,28 @@ def test_launch_list_summary_matches_the_committed_profile():
     rows = [l.split(",") for l in out.strip().splitlines()[1:]]
     assert rows[-1][0] == "TOTAL" and abs(sum(float(r[-1]) for r in rows[:-1]) - 1.0) < 5e-3
     assert any("k_fused_agg_proj" in l for l in out.splitlines()[1:3])            # the dominant kernel the roofline is quoted on
+
+
+def test_compact_wire_format_round_trip_and_device_dataset_on_cpu():
+    """batch.CompactBatch (host -> device wire format) and synthetic.DeviceDataset (resident dataset, on-device collation) are
+    pure index work: run on CPU tensors they must reproduce host collation bit for bit."""
+    import numpy as np
+    from gnn_matlang_b200.batch import CompactBatch
+    from gnn_matlang_b200.synthetic import DeviceDataset, GraphPool
+    fields = ("x", "edge_index2", "edge_attr2", "batch", "y", "graph_ptr")
+    for kind, widths in (("zinc", (21, 4)), ("counting", None)):
+        pool = GraphPool(kind, 24, seed=1)
+        idx = np.random.default_rng(0).integers(0, 24, 60)
+        hb = pool.collate(idx)
+        cb = CompactBatch.from_batch(hb, widths)
+        assert cb.nbytes() < hb.nbytes()
+        b = cb.expand()
+        for k in fields:
+            assert torch.equal(getattr(b, k), getattr(hb, k)), (kind, k)
+        b2 = DeviceDataset(pool, torch.device("cpu")).collate(idx)
+        for k in fields:
+            assert torch.equal(getattr(b2, k), getattr(hb, k)), (kind, k)
+    # a batch whose x is not one-hot refuses the code path instead of silently changing it
+    pool = GraphPool("counting", 8, seed=2)
+    with pytest.raises(ValueError):
+        CompactBatch.from_batch(pool.collate(np.arange(4)), (1, 1))
