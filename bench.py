@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--placeholder-supports", action="store_true", help="N(0,1) edge features instead of SpectralDesign supports")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="enqueue every step's ~120 launches from the host instead of replaying "
+                                                                  "the captured step")
     return ap.parse_args()
 
 
@@ -292,23 +294,34 @@ def time_steps(trainer, batches, steps, warmup, barrier):
 
 
 def small_config(dev, workload, B, steps, warmup, supports=True):
-    """One of the other BASELINE.json configurations at its own batch size, bounded: -> dict for `other_configs`."""
+    """One of the other BASELINE.json configurations at its own batch size, bounded: -> dict for `other_configs`.  At these
+    sizes the step is launch-bound: reported both enqueued launch by launch and as ONE captured CUDA graph replayed per step."""
     from gnn_matlang_b200.models import GNNML3
     from gnn_matlang_b200.synthetic import GraphPool
-    from gnn_matlang_b200.train import Trainer
+    from gnn_matlang_b200.train import GraphedTrainer, Trainer, pad_batch, padded_shapes
     kind, cfg, loss, _, desc, _ = WORKLOADS[workload]
     pool = GraphPool(kind, 512, seed=5)
     if supports:
         pool.attach_spectral_supports(dev)
     rng = np.random.default_rng(11)
-    ring = [pool.draw(rng, B).to(dev, non_blocking=False) for _ in range(8)]
+    host = [pool.draw(rng, B) for _ in range(8)]
+    ring = [hb.to(dev, non_blocking=False) for hb in host]
     torch.manual_seed(0)
     model = GNNML3(cfg, pool.K, pool.F).to(dev)
     trainer = Trainer(model, loss=loss, lr=1e-3)
     ms, host_ms, loss_t = time_steps(trainer, lambda i: ring[i % len(ring)].fresh(), steps, warmup, torch.cuda.synchronize)
-    return {"reference_script": desc, "graphs_per_step": B, "steps": steps, "ms_per_step": ms / steps, "graphs_per_s": B * steps / (ms * 1e-3),
-            "host_enqueue_ms_per_step": host_ms, "edge_attr": pool.supports, "final_loss": float(loss_t.item()),
-            "note": "launch-bound at the reference's batch size: the step is ~120 launches of a few microseconds each"}
+    Np, Ep = padded_shapes(host)
+    pads = [pad_batch(hb, Np, Ep).to(dev, non_blocking=False) for hb in host]
+    torch.manual_seed(0)
+    model2 = GNNML3(cfg, pool.K, pool.F).to(dev)
+    gt = GraphedTrainer(model2, pads[0], loss=loss, lr=1e-3)
+    ms_g, host_g, loss_g = time_steps(gt, lambda i: pads[i % len(pads)], steps, warmup, torch.cuda.synchronize)
+    return {"reference_script": desc, "graphs_per_step": B, "steps": steps, "edge_attr": pool.supports,
+            "cuda_graph": {"ms_per_step": ms_g / steps, "graphs_per_s": B * steps / (ms_g * 1e-3), "host_enqueue_ms_per_step": host_g,
+                           "final_loss": float(loss_g.item())},
+            "launch_by_launch": {"ms_per_step": ms / steps, "graphs_per_s": B * steps / (ms * 1e-3), "host_enqueue_ms_per_step": host_ms,
+                                 "final_loss": float(loss_t.item())},
+            "ms_per_step": ms_g / steps, "graphs_per_s": B * steps / (ms_g * 1e-3)}
 
 
 def exp_config(dev, B, steps, warmup, cpu_sample=True):
@@ -441,36 +454,74 @@ def main():
 
     torch.manual_seed(0)             # identical replicas
     model = GNNML3(cfg, pool.K, pool.F, precision=args.precision).to(dev)
-    trainer = Trainer(model, loss=loss, lr=1e-3, distributed=world > 1)
+    use_graph = not args.no_cuda_graph and not is_exp
+    from gnn_matlang_b200.train import GraphedTrainer, pad_batch, padded_shapes
+    if use_graph:
+        # static shapes for the captured step: every ring batch padded (neutral padding, train.pad_batch) to the ring's largest
+        Np, Ep = padded_shapes(host_ring)
+        pad_ring = [pad_batch(hb, Np, Ep).to(dev, non_blocking=False) for hb in host_ring]
+        trainer = GraphedTrainer(model, pad_ring[0], loss=loss, lr=1e-3, distributed=world > 1)
+        run_step = lambda i: trainer.step(pad_ring[i % args.ring])
+        pad_note = ("step captured in ONE CUDA graph and replayed; batches padded to %d nodes / %d entries (%.1f %% / %.1f %% neutral "
+                    "padding), the new batch is copied device->device into the captured buffers inside the timed region"
+                    % (Np, Ep, 100.0 * (Np - N0) / Np, 100.0 * (Ep - E0) / Ep))
+    else:
+        trainer = Trainer(model, loss=loss, lr=1e-3, distributed=world > 1)
+        run_step = lambda i: trainer.step(get_batch(i))
+        pad_note = "every launch enqueued from the host (no CUDA graph)"
 
     # ---- warm-up
     for i in range(max(args.warmup, 3)):
-        trainer.step(get_batch(i))
+        run_step(i)
     barrier()
 
     # ---- timed region: inputs resident in HBM; successive steps use different batches (ring > L2)
     sampler = ClockSampler(local)
     sampler.start()
-    lib.gnnml3_fused_profile(1)          # CUDA events around every fused layer-kernel launch, on the launching stream
-    ops.fused_path_counts(reset=True)
-    n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     th0 = time.perf_counter()
     for i in range(args.steps):
-        loss_t = trainer.step(get_batch(i))
+        loss_t = run_step(i)
     host_ms = (time.perf_counter() - th0) * 1e3 / args.steps      # CPU time to ENQUEUE a step (no sync inside the loop)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - n0
+    final_loss = float(loss_t.item())
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- the same step enqueued launch by launch (identical kernels and batches; a captured graph cannot carry timing events):
+    #      per-launch CUDA events around the dominant kernel for the roofline, launch count, fused-path counters
+    eager = Trainer(model, loss=loss, lr=1e-3, distributed=world > 1) if use_graph else trainer
+    nprof = min(args.steps, 10)
+    for i in range(2):
+        eager.step(get_batch(i))
+    barrier()
+    lib.gnnml3_fused_profile(1)          # CUDA events around every fused layer-kernel launch, on the launching stream
+    ops.fused_path_counts(reset=True)
+    n0 = _lib.launch_count()
+    e0.record()
+    th0 = time.perf_counter()
+    for i in range(nprof):
+        eager.step(get_batch(i))
+    eager_host_ms = (time.perf_counter() - th0) * 1e3 / nprof
+    e1.record()
+    barrier()
+    eager_ms = e0.elapsed_time(e1) / nprof
+    launches = (_lib.launch_count() - n0) // nprof
     paths = ops.fused_path_counts()
     import ctypes
     pbuf = (ctypes.c_double * (10 * 4096))()
     nrec = lib.gnnml3_fused_profile_fetch(pbuf, 4096)
     lib.gnnml3_fused_profile(0)
-    per_step = nrec // max(args.steps, 1)
+    per_step = nrec // max(nprof, 1)
     recs = []
     for j in range(nrec):
         msj, Nn, Kk, Ff, Ncc, Fss, smode, Nss, Gg, hp = [pbuf[j * 10 + t] for t in range(10)]
@@ -482,16 +533,9 @@ def main():
                         + Fss * (Nss if smode == 1 else (Ncc if smode == 2 else 0)) + Ncc + Nn * (Ncc + (Gg if smode == 1 else 0))
                         + (Nn * 2 * Gg if smode == 1 else 0))
         recs.append((msj, nbytes))
-    sampler.stop_flag = True
-    sampler.join()
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * B * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (the fused aggregate+project layer kernel: forward launches and the transposed
-    #      dx launches of the backward), from the per-launch CUDA events of the timed region.
+    #      dx launches of the backward)
     pk = peaks()
     peak = float(pk.get("hbm_gbs", 6650.0))
     sp_ms = sum(r[0] for r in recs)
@@ -509,19 +553,30 @@ def main():
                     "bound": "hbm", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in pk else "fallback 6650",
-                    "launches": len(recs), "avg_launch_ms": sp_ms / len(recs), "share_of_step": sp_ms / ms,
+                    "launches": len(recs), "avg_launch_ms": sp_ms / len(recs), "share_of_step": sp_ms / nprof / eager_ms,
                     "algorithmic_bytes_per_launch": sp_bytes / len(recs),
+                    "measured_in": "%d steps of the same training step enqueued launch by launch right after the timed region (CUDA "
+                                   "events on the launching stream inside gnnml3_fused_agg_proj)" % nprof,
                     "note": "FP32 FMA issue of the aggregation (about 60 % SIMD efficiency over ragged rows) + per-tile hand-off, see DESIGN.md section 4"}
 
-    # ---- end to end: host (pinned) batches through Trainer; H2D of every step's inputs + D2H of the loss inside
+    # ---- end to end: pinned host batches in the compact wire format -> H2D on a copy stream (one step ahead) -> rebuilt on the
+    #      device -> written into the captured buffers -> graph replay; D2H of every step's loss inside the timed region
     e2e = None
     if not args.no_e2e and not is_exp:
         feeder = HostFeeder(dev, onehot_widths=(21, 4) if kind == "zinc" else None)
+        for hb in host_ring:
+            feeder.compact(hb)                  # wire-format conversion = data preparation, like collation: outside the timed region
+        if use_graph:
+            def e2e_step(b):
+                trainer.load_unpadded(b)
+                return trainer.step()
+        else:
+            e2e_step = trainer.step
         feeder.prefetch(host_ring[0])
         for i in range(3):
             b = feeder.get()
             feeder.prefetch(host_ring[(i + 1) % args.ring])
-            float(trainer.step(b).item())
+            float(e2e_step(b).item())
         barrier()
         e0.record()
         # every step's loss is read back to the host: the device -> host copy is enqueued right behind the step (pinned
@@ -532,7 +587,7 @@ def main():
         for i in range(args.steps):
             b = feeder.get()
             feeder.prefetch(host_ring[(i + 4) % args.ring])
-            lt = trainer.step(b)
+            lt = e2e_step(b)
             loss_host[i & 1].copy_(lt.reshape(1), non_blocking=True)      # device -> host read of the step's loss
             loss_ev[i & 1].record()
             if i > 0:
@@ -554,13 +609,19 @@ def main():
         # variant: the dataset (pool) resident in HBM, collation on the device; the step's host input is the graph-id list
         from gnn_matlang_b200.synthetic import DeviceDataset
         dds = DeviceDataset(pool, dev)
-        idx_host = [torch.from_numpy(rng.integers(0, len(pool.n), B).astype(np.int64)).pin_memory() for _ in range(args.ring)]
+        idx_host = []
+        for _ in range(args.ring):
+            while True:                          # (draws that fit the captured shapes)
+                idx = rng.integers(0, len(pool.n), B)
+                if not use_graph or (pool.n[idx].sum() < Np and Ep - 8 * (Np - pool.n[idx].sum()) <= pool.e[idx].sum() <= Ep):
+                    break
+            idx_host.append(torch.from_numpy(idx.astype(np.int64)).pin_memory())
         for i in range(3):
-            float(trainer.step(dds.collate(idx_host[i % args.ring])).item())
+            float(e2e_step(dds.collate(idx_host[i % args.ring])).item())
         barrier()
         e0.record()
         for i in range(args.steps):
-            lt = trainer.step(dds.collate(idx_host[i % args.ring]))
+            lt = e2e_step(dds.collate(idx_host[i % args.ring]))
             loss_host[i & 1].copy_(lt.reshape(1), non_blocking=True)
             loss_ev[i & 1].record()
             if i > 0:
@@ -632,11 +693,13 @@ def main():
             "metric": "GNNML3 train graphs/s", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
-            "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "host_enqueue_ms_per_step": host_ms,
-            "path_taken": {"fused_layer_launches_tensor_memory_kernel": paths[0], "fused_layer_launches_smem_plane_kernel": paths[1],
-                           "per_step": [paths[0] / args.steps, paths[1] / args.steps]},
-            "kernel_shares_one_step": ncu_shares(), "other_configs": other, "final_loss": float(loss_t.item())}), flush=True)
+            "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+            "clocks": sampler.summary(), "host_enqueue_ms_per_step": host_ms, "step_mode": pad_note,
+            "eager_step": {"ms_per_step": eager_ms, "host_enqueue_ms_per_step": eager_host_ms,
+                           "note": "the same step enqueued launch by launch (no CUDA graph)"} if use_graph else None,
+            "path_taken": {"fused_layer_launches_tensor_memory_kernel": paths[0] // nprof, "fused_layer_launches_smem_plane_kernel": paths[1] // nprof,
+                           "unit": "launches per step"},
+            "kernel_shares_one_step": ncu_shares(), "other_configs": other, "final_loss": final_loss}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -102,3 +102,123 @@ class HostFeeder(object):
             v.record_stream(torch.cuda.current_stream())
         self._next = None
         return b.expand()
+
+
+def pad_batch(hb, n_nodes, n_entries):
+    """Host ``Batch`` -> the same batch padded to ``n_nodes`` nodes and ``n_entries`` support entries (static shapes for CUDA
+    graph replay).  The padding is exactly neutral: the extra nodes are isolated, carry zero features and form ONE extra
+    (dummy) graph at the end whose read-out row the loss never sees (``GraphedTrainer`` slices it off); the extra entries are
+    self-loops spread round-robin over the dummy nodes with all-zero supports (a bias-free edge MLP maps them to zero, they
+    add 0 to those nodes and receive zero gradients).  ``n_nodes`` must exceed the batch's node count (the dummy graph is
+    never empty); ``padded_shapes`` picks shapes that keep the dummy nodes' degree small (a hub row would serialise the
+    row-parallel kernels)."""
+    import numpy as np
+    from .batch import Batch
+    N, E = hb.x.size(0), hb.edge_index2.size(1)
+    if n_nodes <= N or n_entries < E:
+        raise ValueError("pad_batch: need n_nodes > %d and n_entries >= %d" % (N, E))
+    B = hb.num_graphs
+    x = torch.zeros(n_nodes, hb.x.size(1), dtype=hb.x.dtype)
+    x[:N] = hb.x
+    ei = torch.empty((2, n_entries), dtype=torch.int64)
+    ei[:, :E] = hb.edge_index2
+    ei[:, E:] = (N + torch.arange(n_entries - E) % (n_nodes - N)).unsqueeze(0)
+    ea = torch.zeros(n_entries, hb.edge_attr2.size(1), dtype=hb.edge_attr2.dtype)
+    ea[:E] = hb.edge_attr2
+    batch = torch.full((n_nodes,), B, dtype=torch.int64)
+    batch[:N] = hb.batch
+    gp = torch.cat([hb.graph_ptr.to(torch.int32), torch.tensor([n_nodes], dtype=torch.int32)])
+    return Batch(x=x, edge_index2=ei, edge_attr2=ea, batch=batch, num_graphs=B + 1, graph_ptr=gp, y=hb.y, real_graphs=B)
+
+
+def padded_shapes(batches, max_pad_degree=8):
+    """(n_nodes, n_entries) for ``pad_batch`` / ``GraphedTrainer`` covering every batch of the list: the largest entry count,
+    and enough dummy nodes that the padding self-loops of the SMALLEST batch give no dummy node more than ``max_pad_degree``."""
+    nmax = max(int(b.x.shape[0]) for b in batches)
+    emax = max(int(b.edge_index2.shape[1]) for b in batches)
+    emin = min(int(b.edge_index2.shape[1]) for b in batches)
+    return nmax + 1 + (emax - emin + max_pad_degree - 1) // max_pad_degree, emax
+
+
+class GraphedTrainer(object):
+    """The whole optimisation step -- CSR build of the new batch, forward, SUM loss, backward, (all-reduce,) Adam -- captured
+    ONCE into a CUDA graph and replayed per step (the step's ~120 launches cost ~2 ms of host time to
+    enqueue, more than the GPU needs at the reference's batch sizes).  Batches must have static shapes (``pad_batch``); a
+    step copies the new batch into the captured input buffers (device -> device, or host -> device when given a pinned host
+    batch) and replays.  Everything inside is capture-safe: the library never synchronises, workspaces are allocated during
+    the warm-up steps, tensor-map descriptors are kernel parameters."""
+
+    def __init__(self, model, example, loss="l1", lr=1e-3, distributed=False, warmup=3):
+        from .graph import set_range_check
+        set_range_check(False)                         # the range check reads a flag back from the device
+        self.model, self.loss_kind = model, loss
+        self.distributed = distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.params = [p for p in model.parameters()]
+        self.opt = torch.optim.Adam(self.params, lr=lr, fused=True, capturable=True)
+        dev = self.params[0].device
+        self.static = example.to(dev, non_blocking=False) if not example.x.is_cuda else example
+        self.real = int(getattr(example, "real_graphs", example.num_graphs))
+        self.fields = ("x", "edge_index2", "edge_attr2", "batch", "graph_ptr", "y")
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._eager_step()
+        self.copy_stream = None
+
+    def _eager_step(self):
+        b = self.static.fresh()
+        for p in self.params:
+            p.grad = None
+        out = self.model(b)
+        loss = loss_fn(self.loss_kind, out[:self.real], b.y)
+        loss.backward()
+        if self.distributed:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            off = 0
+            for p in self.params:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        self.opt.step()
+        return loss.detach()
+
+    def load(self, batch):
+        """Copy a padded batch (device or pinned host, same shapes as the example) into the captured input buffers."""
+        for k in self.fields:
+            getattr(self.static, k).copy_(getattr(batch, k), non_blocking=True)
+
+    def load_unpadded(self, b):
+        """Write a DEVICE batch of any size that fits (N < captured nodes, E <= captured entries, same number of graphs) into the
+        captured input buffers and fill the rest with the neutral padding of ``pad_batch`` (device-side, no host sync)."""
+        st = self.static
+        N, E = b.x.size(0), b.edge_index2.size(1)
+        Np, Ep = st.x.size(0), st.edge_index2.size(1)
+        if N >= Np or E > Ep or b.num_graphs != self.real:
+            raise ValueError("batch (%d nodes, %d entries, %d graphs) does not fit the captured shapes (%d, %d, %d)"
+                             % (N, E, b.num_graphs, Np, Ep, self.real))
+        st.x[:N].copy_(b.x, non_blocking=True)
+        st.x[N:].zero_()
+        st.edge_index2[:, :E].copy_(b.edge_index2, non_blocking=True)
+        if Ep > E:
+            st.edge_index2[:, E:].copy_((N + torch.arange(Ep - E, device=st.x.device) % (Np - N)).unsqueeze(0))
+        st.edge_attr2[:E].copy_(b.edge_attr2, non_blocking=True)
+        st.edge_attr2[E:].zero_()
+        st.batch[:N].copy_(b.batch, non_blocking=True)
+        st.batch[N:].fill_(self.real)
+        st.graph_ptr[:self.real + 1].copy_(b.graph_ptr, non_blocking=True)
+        st.graph_ptr[self.real + 1:].fill_(Np)
+        st.y.copy_(b.y, non_blocking=True)
+
+    def step(self, batch=None):
+        """One optimisation step; returns the (device, captured) loss tensor -- valid until the next step."""
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        return self.static_loss

@@ -44,3 +44,41 @@ def test_device_dataset_collation_bit_exact_and_trains():
     l1 = Trainer(m1, loss="l1").step(b)
     l2 = Trainer(m2, loss="l1").step(hb.to(dev()))
     assert float(l1) == float(l2)
+
+
+def test_captured_step_equals_eager_step_and_padding_is_neutral():
+    """train.GraphedTrainer: the whole optimisation step captured in one CUDA graph and replayed on padded batches gives the
+    same losses and parameters as the eager Trainer on the unpadded batches (padding = one dummy graph of isolated zero nodes +
+    zero-weight self-loops: exactly neutral), through both input routes (padded device batch; unpadded batch written into
+    the captured buffers on the device)."""
+    from gnn_matlang_b200.models import GNNML3
+    from gnn_matlang_b200.synthetic import GraphPool
+    from gnn_matlang_b200.train import GraphedTrainer, Trainer, pad_batch
+    pool = GraphPool("zinc", 64, seed=6)
+    rng = np.random.default_rng(3)
+    host = [pool.draw(rng, 48) for _ in range(4)]
+    Np, Ep = max(h.x.shape[0] for h in host) + 5, max(h.edge_index2.shape[1] for h in host) + 17
+    torch.manual_seed(0)
+    m1 = GNNML3("zinc", pool.K, pool.F).to(dev())
+    torch.manual_seed(0)
+    m2 = GNNML3("zinc", pool.K, pool.F).to(dev())
+    eager = Trainer(m1, loss="l1", lr=1e-3)
+    gt = GraphedTrainer(m2, pad_batch(host[0], Np, Ep), loss="l1", lr=1e-3, warmup=1)
+    # the warm-up step trained m2 and initialised Adam: rewind both IN PLACE (the captured graph holds these tensors' addresses)
+    with torch.no_grad():
+        for a, b in zip(m2.parameters(), m1.parameters()):
+            a.copy_(b)
+        for st in gt.opt.state.values():
+            for v in st.values():
+                if isinstance(v, torch.Tensor):
+                    v.zero_()
+    for i, hb in enumerate(host):
+        l1 = float(eager.step(hb.to(dev())))
+        if i % 2 == 0:
+            l2 = float(gt.step(pad_batch(hb, Np, Ep).to(dev())))
+        else:
+            gt.load_unpadded(hb.to(dev()))
+            l2 = float(gt.step())
+        assert abs(l1 - l2) <= 2e-5 * abs(l1), (i, l1, l2)
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.allclose(a, b, rtol=0, atol=2e-6), k
