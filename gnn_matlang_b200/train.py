@@ -166,26 +166,52 @@ class GraphedTrainer(object):
                 self._eager_step()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
+        # Single process: ONE graph holds the whole step.  Data parallel: the NCCL all-reduce stays outside the capture (a
+        # captured collective ties the graph to the communicator's stream ordering and watchdog); the step is two graphs --
+        # CSR build + forward + loss + backward + gradient flattening | Adam on views of the reduced bucket -- with the one
+        # all-reduce launch between them.
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._eager_step()
-        self.copy_stream = None
+        self.graph2 = None
+        if not self.distributed:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._eager_step()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.static_loss, self.flat = self._fwd_bwd_flat()
+            self._grads_from(self.flat)
+            self.graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
+                self.opt.step()
 
-    def _eager_step(self):
+    def _grads_from(self, flat):
+        off = 0
+        for p in self.params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def _fwd_bwd_flat(self):
         b = self.static.fresh()
         for p in self.params:
             p.grad = None
         out = self.model(b)
         loss = loss_fn(self.loss_kind, out[:self.real], b.y)
         loss.backward()
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        return loss.detach(), torch.cat([g.reshape(-1) for g in grads])
+
+    def _eager_step(self):
         if self.distributed:
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-            flat = torch.cat([g.reshape(-1) for g in grads])
+            loss, flat = self._fwd_bwd_flat()
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            off = 0
-            for p in self.params:
-                p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+            self._grads_from(flat)
+            self.opt.step()
+            return loss
+        b = self.static.fresh()
+        for p in self.params:
+            p.grad = None
+        out = self.model(b)
+        loss = loss_fn(self.loss_kind, out[:self.real], b.y)
+        loss.backward()
         self.opt.step()
         return loss.detach()
 
@@ -221,4 +247,7 @@ class GraphedTrainer(object):
         if batch is not None:
             self.load(batch)
         self.graph.replay()
+        if self.graph2 is not None:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.graph2.replay()
         return self.static_loss

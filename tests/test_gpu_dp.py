@@ -34,11 +34,14 @@ def _worker(rank, world, port, out_path):
     model = GNNML3("zinc", pool.K, pool.F).to(dev)
     tr = Trainer(model, loss="l1", lr=1e-3, distributed=True)
     per = B // world
+    grads = None
     for idx in _batches(pool):
         tr.step(pool.collate(idx[rank * per:(rank + 1) * per]).to(dev))
+        if grads is None:                  # all-reduced gradient of the first step (a view of the reduced bucket)
+            grads = {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()}
     torch.cuda.synchronize()
     if rank == 0:
-        torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, out_path)
+        torch.save(({k: v.detach().cpu() for k, v in model.state_dict().items()}, grads), out_path)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -54,22 +57,34 @@ def test_two_ranks_on_half_batches_equal_one_rank_on_full_batches():
         out = os.path.join(d, "dp.pt")
         port = 29500 + os.getpid() % 2000
         mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
-        dp = torch.load(out)
+        dp, dp_grads = torch.load(out)
     dev = torch.device("cuda", 0)
     pool = GraphPool("zinc", 96, seed=9)
     torch.manual_seed(0)
     model = GNNML3("zinc", pool.K, pool.F).to(dev)
     init = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     tr = Trainer(model, loss="l1", lr=1e-3, distributed=False)
-    for idx in _batches(pool):
+    gworst = 0.0
+    for s, idx in enumerate(_batches(pool)):
         tr.step(pool.collate(idx).to(dev))
+        if s == 0:
+            # the all-reduced gradient of two half-batches IS the full-batch gradient (SUM losses): only the summation order
+            # differs.  FP32 bar 1e-5 relative to the tensor's scale.
+            for k, p in model.named_parameters():
+                a, b = dp_grads[k].double(), p.grad.detach().cpu().double()
+                err, scale = (a - b).abs().max().item(), b.abs().max().item()
+                gworst = max(gworst, err / max(scale, 1e-30))
+                assert err <= 1e-5 * scale + 1e-12, "grad %s: 2-rank vs 1-rank differ by %.3e (max|grad| %.3e)" % (k, err, scale)
     worst = 0.0
     for k, v in model.state_dict().items():
         a, b = dp[k].double(), v.detach().cpu().double()
         moved = (b - init[k].double()).abs().max().item()
         assert moved > 0, "parameter %s did not train" % k
-        # two Adam steps move every weight by ~2e-3; the two runs differ only by the summation order of the gradient
+        # Adam normalises every element by its own gradient history, so elements whose gradient nearly cancels amplify the
+        # 1e-6 summation-order noise: the parameters are held to 10 % of the update size (2 steps x lr), the gradients above
+        # to the FP32 bar
         err = (a - b).abs().max().item()
         worst = max(worst, err / moved)
-        assert err <= 2e-3 * moved + 1e-7, "%s: 2-rank vs 1-rank differ by %.3e (update size %.3e)" % (k, err, moved)
-    print("2-rank vs 1-rank parameters after %d steps: worst |diff| / |update| = %.3e" % (STEPS, worst))
+        assert err <= 0.1 * moved, "%s: 2-rank vs 1-rank differ by %.3e (update size %.3e)" % (k, err, moved)
+    print("2-rank vs 1-rank: first-step gradients worst |diff| / max|grad| = %.3e; parameters after %d steps worst |diff| / |update| "
+          "= %.3e" % (gworst, STEPS, worst))

@@ -2,6 +2,8 @@
 totals for ONE training step (the last complete step of the capture).
 
 usage: python tools/summarise_launches.py raw.csv n_steps_total > one_step.csv
+       python tools/summarise_launches.py raw.csv --marker k_csr_hist > one_step.csv     (a step starts at every launch of the
+                                                       marker kernel: the CSR build opens each training step; takes the last step)
 """
 import collections
 import csv
@@ -20,9 +22,13 @@ def short(name):
 
 def main():
     rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
-    steps = int(sys.argv[2])
-    per = len(rows) // steps
-    last = rows[len(rows) - per:]
+    if sys.argv[2] == "--marker":
+        starts = [i for i, r in enumerate(rows) if sys.argv[3] in r[4]]
+        last = rows[starts[-1]:]
+    else:
+        steps = int(sys.argv[2])
+        per = len(rows) // steps
+        last = rows[len(rows) - per:]
     tot = collections.OrderedDict()
     for r in last:
         k = short(r[4])
