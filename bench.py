@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU per step (0 = workload default)")
     ap.add_argument("--pool", type=int, default=2048, help="distinct synthetic graphs in the pool")
     ap.add_argument("--ring", type=int, default=6, help="distinct resident batches cycled through (> L2 in total)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
@@ -687,13 +687,13 @@ def main():
         edge_attr = pool.supports if not is_exp else ExpPool.supports
         config = common_config(args.workload, B, desc, edge_attr)
         config.update({"graphs_per_step_all_gpus": B * world, "nodes_per_step_per_gpu": N0, "support_entries_per_step_per_gpu": E0, "K": pool.K,
-                       "gemm_arithmetic": "3xTF32 (FP32-grade)" if args.precision == "fp32" else "TF32",
+                       "gemm_arithmetic": {"fp32": "3xTF32 (FP32-grade)", "tf32": "single-pass TF32 (flagged)", "bf16": "BF16 projection in the fused layer kernel, TF32 elsewhere (flagged)"}[args.precision],
                        "sharding": "whole graphs over %d rank(s), one gradient SUM all-reduce per step" % world,
                        "l2_policy": "ring of %d distinct resident batches, %.0f MB in total (> 126 MB L2)" % (args.ring, args.ring * batch_bytes / 1e6)})
         print(json.dumps({
             "metric": "GNNML3 train graphs/s", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
             "clocks": sampler.summary(), "host_enqueue_ms_per_step": host_ms, "step_mode": pad_note,
             "eager_step": {"ms_per_step": eager_ms, "host_enqueue_ms_per_step": eager_host_ms,

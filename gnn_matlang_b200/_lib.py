@@ -28,6 +28,7 @@ SIGNATURES = {
     "gnnml3_gather_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
     "gnnml3_scatter_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
     "gnnml3_spmm_k": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p, _i64, _p]),
+    "gnnml3_spmm_projected": (_i, [_p, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p, _i64, _p]),
     "gnnml3_sddmm_k": (_i, [_p, _p, _p, _p, _i64, _p, _i64, _i64, _i, _i, _p, _p]),
     "gnnml3_gemm_nn": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _i, _p]),
     "gnnml3_gemm_tn_workspace_bytes": (_sz, [_i64, _i, _i]),
@@ -78,6 +79,8 @@ SIGNATURES = {
 
 PREC_3XTF32 = 0
 PREC_TF32 = 1
+PREC_BF16 = 2          # fused layer kernel only (GNNML3_FUSED_BF16); the stand-alone GEMMs run it as single-pass TF32
+FUSED_FLAGS = {0: 0, 1: 0x100, 2: 0x200}
 EPI_NONE = 0
 EPI_RELU = 1
 

@@ -1056,7 +1056,12 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
     GNNML3_REQUIRE((uintptr_t)ea % 16 == 0, "fused_agg_proj: ea must be 16-byte aligned");
     GNNML3_REQUIRE(self_mode == 0 || (S && Bself && lds % 4 == 0 && (uintptr_t)S % 16 == 0),
                    "fused_agg_proj: self block needs S, Bself and 16-byte aligned rows");
+    const int prec_bits = epilogue & 0x300;                  // GNNML3_FUSED_TF32 / GNNML3_FUSED_BF16 (tensor-memory kernel only)
+    epilogue &= 0xff;
     GNNML3_REQUIRE(epilogue == 0 || epilogue == 1, "fused_agg_proj: unknown epilogue");
+    GNNML3_REQUIRE(prec_bits == 0 || prec_bits == 0x100 || prec_bits == 0x200, "fused_agg_proj: unknown precision flag");
+    GNNML3_REQUIRE(prec_bits == 0 || (gnnml3_fused_ts_supported(K, Kstride, F, Nc, Fs, self_mode, Ns) && g_fl_slot_mode == 0),
+                   "fused_agg_proj: the single-pass TF32 / BF16 modes exist in the tensor-memory kernel only (F <= 32, even K)");
     GNNML3_REQUIRE(self_mode != 1 || (epilogue == 1 && aux && G >= 1 && G <= 16 && Ns == 2 * G),
                    "fused_agg_proj: gate columns need the ML3 epilogue, aux and Ns == 2G <= 32");
     GNNML3_REQUIRE(ldo >= Nc + (self_mode == 1 ? G : 0), "fused_agg_proj: ldo too small");
@@ -1082,7 +1087,7 @@ extern "C" int gnnml3_fused_agg_proj(const int32_t* rowptr, const int32_t* col, 
             cudaEventRecord(rec.a, st);
         }
         const int rc = fused_ts_run(rowptr, col, eperm, ea, Kstride, K, X, ldx, F, S, lds, Fs, self_mode, Bmain, ldb, Bself, ldbs, Ns, bias,
-                                    bias_s, N, Nc, out, ldo, aux, ldaux, G, epilogue, hout, ldh, tilewin, workspace, workspace_bytes,
+                                    bias_s, N, Nc, out, ldo, aux, ldaux, G, epilogue | prec_bits, hout, ldh, tilewin, workspace, workspace_bytes,
                                     g_fl_dbg, st);
         if (g_fl_prof_on) {
             cudaEventRecord(rec.b, st);

@@ -25,6 +25,7 @@
 // Summation order per row = edge order of the CSR row (the reference's CPU scatter order); no atomics.
 #include "tc_common.cuh"
 
+#include <cuda_bf16.h>
 #include <vector>
 
 namespace gnnml3 {
@@ -69,6 +70,7 @@ struct TSParams {
     int64_t ldaux;
     int G;
     int epi;                // 0 plain (+bias) | 1 ml3: relu on the main columns, tanh*tanh gating on the self columns
+    int prec;               // 0 FP32-grade 3xTF32 | 1 single-pass TF32 | 2 BF16 inputs (both: FP32 accumulate, no residual blocks)
     float* hout;            // optional copy of the aggregate [N, ldh]: support k at column 32 k, self block behind
     int64_t ldh;
     unsigned long long* dbg;
@@ -147,6 +149,12 @@ __device__ __forceinline__ void ts_st_16x64b_x16(uint32_t taddr, const float* v)
                  "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
                  : "memory");
 }
+// 16 TMEM lanes x 16 columns (same thread <-> lane / column-parity map, 8 registers)
+__device__ __forceinline__ void ts_st_16x64b_x8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.16x64b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void ts_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // tensor-memory loads without the trailing wait (several loads, then one ts_ld_wait)
@@ -180,6 +188,29 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// same with BF16 inputs (kind::f16, K = 16 per instruction: two BF16 per 32-bit tensor-memory column), FP32 accumulate
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// instruction descriptor of tcgen05.mma kind::f16 with BF16 A / B (K-major) and FP32 D
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// this thread's 16 features of a block -> 8 packed BF16 pairs (features 2j, 2j+1 of the thread's 16 in register j)
+__device__ __forceinline__ void ts_pack_bf16(const float* v, uint32_t (&r)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        r[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
 }
 
 template <int KT>
@@ -446,11 +477,22 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUt
                 const bool gate = P.self_mode == 1 && kb == P.nkb_main;
                 const uint32_t d = gate ? d_main + 64 : d_main;
                 if (ts_elect_one()) {
+                    if (P.prec == 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 32) >> 4);     // 8 TF32 = 32 bytes along K inside the swizzled row
-                        umma_tf32_ts(d, a_raw + 8 * k, dw + adv, ID_FULL, ((gate || kb == 0) && k == 0) ? 0u : 1u);
-                        umma_tf32_ts(d + BNH, a_lo + 8 * k, dw + adv, ID_HALF, 1u);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);     // 8 TF32 = 32 bytes along K inside the swizzled row
+                            umma_tf32_ts(d, a_raw + 8 * k, dw + adv, ID_FULL, ((gate || kb == 0) && k == 0) ? 0u : 1u);
+                            umma_tf32_ts(d + BNH, a_lo + 8 * k, dw + adv, ID_HALF, 1u);
+                        }
+                    } else if (P.prec == 1) {                                   // single-pass TF32: hi weights only (first BNH plane rows)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_tf32_ts(d, a_raw + 8 * k, dw + (uint64_t)((k * 32) >> 4), ID_HALF, ((gate || kb == 0) && k == 0) ? 0u : 1u);
+                    } else {                                                    // BF16: 16 k-elements (8 packed columns, 32 bytes) per MMA
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            umma_bf16_ts(d, a_raw + 8 * k, dw + (uint64_t)((k * 32) >> 4), make_idesc_bf16(128, BNH),
+                                         ((gate || kb == 0) && k == 0) ? 0u : 1u);
                     }
                     umma_commit(empty + s);
                     if (kb == nkb_total - 1) umma_commit(tfull);
@@ -488,7 +530,12 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUt
             for (int c0 = 0; c0 < BNH; c0 += 32) {
                 float vh[32], vl[32];
                 ts_tmem_ld32_nw(taddr + c0, vh);
-                ts_tmem_ld32_nw(taddr + BNH + c0, vl);
+                if (P.prec == 0) {
+                    ts_tmem_ld32_nw(taddr + BNH + c0, vl);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) vl[i] = 0.f;
+                }
                 ts_ld_wait();
                 if (live) {
 #pragma unroll
@@ -515,8 +562,13 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUt
                 float g1h[16], g2h[16], g1l[16], g2l[16];
                 ts_tmem_ld16_nw(taddr + 64, g1h);
                 ts_tmem_ld16_nw(taddr + 80, g2h);
-                ts_tmem_ld16_nw(taddr + 96, g1l);
-                ts_tmem_ld16_nw(taddr + 112, g2l);
+                if (P.prec == 0) {
+                    ts_tmem_ld16_nw(taddr + 96, g1l);
+                    ts_tmem_ld16_nw(taddr + 112, g2l);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) g1l[i] = g2l[i] = 0.f;
+                }
                 ts_ld_wait();
                 if (live) {
                     float* ax = P.aux + r * P.ldaux;
@@ -709,11 +761,19 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < KT; ++k) {
                         const uint32_t ta = tmem_base + lane_addr + TS_SLOT0 + si * 64;
-                        float lo[16];
+                        if (P.prec == 2) {
+                            uint32_t pk[8];
+                            ts_pack_bf16(acc[k], pk);
+                            ts_st_16x64b_x8(ta, pk);
+                        } else {
+                            ts_st_16x64b_x16(ta, acc[k]);
+                            if (P.prec == 0) {
+                                float lo[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) lo[i] = ts_lo(acc[k][i]);
-                        ts_st_16x64b_x16(ta, acc[k]);
-                        ts_st_16x64b_x16(ta + 32, lo);
+                                for (int i = 0; i < 16; ++i) lo[i] = ts_lo(acc[k][i]);
+                                ts_st_16x64b_x16(ta + 32, lo);
+                            }
+                        }
                         if (++si == TS_NSLOT) si = 0;
                     }
                     ts_st_wait();
@@ -734,16 +794,24 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUt
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) st_na4(hr + i, make_float4(sv[i], sv[i + 1], sv[i + 2], sv[i + 3]));
                     }
-                    float lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) lo[i] = ts_lo(sv[i]);
                     TS_CNT(const long long cw = clock64();)
                     mbar_wait(empty + st_i, st_ph);
                     TS_CNT(c_wait += clock64() - cw;)
                     tc_fence_after();
                     const uint32_t ta = tmem_base + lane_addr + TS_SLOT0 + st_i * 64;
-                    ts_st_16x64b_x16(ta, sv);
-                    ts_st_16x64b_x16(ta + 32, lo);
+                    if (P.prec == 2) {
+                        uint32_t pk[8];
+                        ts_pack_bf16(sv, pk);
+                        ts_st_16x64b_x8(ta, pk);
+                    } else {
+                        ts_st_16x64b_x16(ta, sv);
+                        if (P.prec == 0) {
+                            float lo[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) lo[i] = ts_lo(sv[i]);
+                            ts_st_16x64b_x16(ta + 32, lo);
+                        }
+                    }
                     ts_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -776,8 +844,11 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUt
 // column c holds feature f(c) = 16 * (c & 1) + (c >> 1) of the block (the tensor-memory column order of the aggregators).
 // Self plane: mode 2 -> Bself [Fs, Nc]; mode 1 -> the gate weights Bself [Fs, Ns = 2G] = [W11^T | W12^T]: p1_j in plane row j,
 // p2_j in plane row 16 + j (so the epilogue pairs accumulator columns j and 16 + j whatever G is).
+// prec 2 (BF16): plane row n = 64 BF16 slots (the same 128 bytes), slot kappa < 32 holds feature 16 * ((kappa >> 1) & 1) +
+// 2 * (kappa >> 2) + (kappa & 1) -- the order in which the aggregators pack their accumulators into tensor memory; rows
+// >= BNH unused.
 __global__ void k_ts_prep_weights(const float* __restrict__ Bmain, int64_t ldb, int K, int F, int Nc, int BNH,
-                                  const float* __restrict__ Bself, int64_t ldbs, int Fs, int Ns, int self_mode,
+                                  const float* __restrict__ Bself, int64_t ldbs, int Fs, int Ns, int self_mode, int prec,
                                   float* __restrict__ planes) {
     const int nkb_total = K + (self_mode != 0 ? 1 : 0);
     const int MR = 2 * BNH;
@@ -786,7 +857,7 @@ __global__ void k_ts_prep_weights(const float* __restrict__ Bmain, int64_t ldb, 
         const int kb = i / (MR * 32), m = (i / 32) % MR, c = i % 32;
         const int n = m % BNH;
         const bool is_lo = m >= BNH;
-        const int f = 16 * (c & 1) + (c >> 1);
+        const int f = prec == 2 ? 16 * ((c >> 1) & 1) + 2 * (c >> 2) + (c & 1) : 16 * (c & 1) + (c >> 1);
         float v = 0.f;
         if (kb < K) {
             if (f < F && n < Nc) v = __ldg(Bmain + ((int64_t)kb * F + f) * ldb + n);
@@ -796,8 +867,14 @@ __global__ void k_ts_prep_weights(const float* __restrict__ Bmain, int64_t ldb, 
             const int j = n & 15, which = n >> 4, G = Ns >> 1;      // plane row j: p1_j, row 16 + j: p2_j
             if (f < Fs && j < G) v = __ldg(Bself + (int64_t)f * ldbs + which * G + j);
         }
-        const float h = tf32_rn(v);
-        planes[i] = is_lo ? v - h : h;
+        if (prec == 2) {
+            __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(planes + (size_t)(kb * MR + m) * 32);
+            row[c] = __float2bfloat16_rn(is_lo ? 0.f : v);
+            row[32 + c] = __float2bfloat16_rn(0.f);
+        } else {
+            const float h = tf32_rn(v);
+            planes[i] = is_lo ? v - h : h;
+        }
     }
 }
 
@@ -952,6 +1029,8 @@ int fused_ts_run(const int32_t* rowptr, const int32_t* col, const int32_t* eperm
                  const float* Bself, int64_t ldbs, int Ns, const float* bias, const float* bias_s, int64_t N, int Nc, float* out,
                  int64_t ldo, float* aux, int64_t ldaux, int G, int epilogue, float* hout, int64_t ldh, const int32_t* tilewin,
                  void* workspace, size_t workspace_bytes, unsigned long long* dbg, cudaStream_t st) {
+    const int prec = (epilogue >> 8) & 3;
+    epilogue &= 0xff;
     if (workspace_bytes < gnnml3_fused_ts_workspace_bytes(K, Nc, self_mode))
         return set_err(GNNML3_ERR_WORKSPACE, "fused_agg_proj: workspace too small");
     const int BNH = Nc <= 32 ? 32 : 64;
@@ -961,7 +1040,7 @@ int fused_ts_run(const int32_t* rowptr, const int32_t* col, const int32_t* eperm
     {
         const int total = nkb_total * 2 * BNH * 32;
         const int blocks = cdiv(total, 256) > 592 ? 592 : cdiv(total, 256);
-        k_ts_prep_weights<<<blocks, 256, 0, st>>>(Bmain, ldb, K, F, Nc, BNH, Bself, ldbs, Fs, Ns, self_mode, planes);
+        k_ts_prep_weights<<<blocks, 256, 0, st>>>(Bmain, ldb, K, F, Nc, BNH, Bself, ldbs, Fs, Ns, self_mode, prec, planes);
         GNNML3_LAUNCH_CHECK();
     }
     CUtensorMap mW, mX;
@@ -973,7 +1052,7 @@ int fused_ts_run(const int32_t* rowptr, const int32_t* col, const int32_t* eperm
     P.rowptr = rowptr; P.col = col; P.eperm = eperm; P.ea = ea; P.Kstride = Kstride; P.K = K;
     P.X = X; P.ldx = ldx; P.F = F; P.S = S; P.lds = lds; P.Fs = Fs; P.self_mode = self_mode;
     P.N = N; P.n_tiles = cdiv(N, TS_ROWS); P.nkb_main = K; P.tilewin = reinterpret_cast<const int2*>(tilewin); P.win_rows = win_rows;
-    P.bias = bias; P.bias_s = bias_s; P.out = out; P.ldo = ldo; P.Nc = Nc; P.aux = aux; P.ldaux = ldaux; P.G = G; P.epi = epilogue;
+    P.bias = bias; P.bias_s = bias_s; P.out = out; P.ldo = ldo; P.Nc = Nc; P.aux = aux; P.ldaux = ldaux; P.G = G; P.epi = epilogue; P.prec = prec;
     P.hout = hout; P.ldh = ldh; P.dbg = dbg;
     P.edge_cap = tilewin ? ts_edge_cap(K, Kstride, Nc, self_mode) : 0;
     const size_t smem = ts_smem_bytes(K, Kstride, Nc, self_mode, P.edge_cap);

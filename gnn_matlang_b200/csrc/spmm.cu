@@ -390,3 +390,62 @@ extern "C" int gnnml3_sddmm_k(const int32_t* rowptr, const int32_t* col, const i
     }
     return GNNML3_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Project-first order of SpectConv (north_star: "or alternatively pre-projects and then aggregates, chosen by F_in/F_out"):
+//   Y = x [W_0 .. W_{K-1}]  ([N, K*Fo], one tensor-core GEMM),  out[t, :] = sum_{p in row t} sum_k ea[e(p), k] * Y[col[p], k*Fo : (k+1)*Fo] (+ bias)
+// Same mathematics as libs/spect_conv.py:70-80 with the sum over k moved inside the edge sum.  It gathers K*Fo floats per
+// support entry instead of Fi, so it wins when the layer narrows (K*Fo*(E + 2N) < Fi*(E + 2NK) in HBM words).
+// One warp per row, lanes over the output features (coalesced reads of the gathered Y rows), edge order, no atomics.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace gnnml3 {
+
+template <int FPL>      // output features per lane (Fo <= 32 * FPL)
+__global__ void __launch_bounds__(256) k_spmm_projected(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ eperm,
+                                                        const float* __restrict__ ea, int K, const float* __restrict__ Y, int64_t ldy, int N,
+                                                        int Fo, const float* __restrict__ bias, float* __restrict__ out, int64_t ldo) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= N) return;
+    const int rs = __ldg(rowptr + warp), re = __ldg(rowptr + warp + 1);
+    float acc[FPL];
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) acc[i] = 0.f;
+    for (int p = rs; p < re; ++p) {
+        const int s = __ldg(col + p);
+        const int e = eperm ? __ldg(eperm + p) : p;
+        const float* yr = Y + (int64_t)s * ldy;
+        const float* wr = ea + (int64_t)e * K;
+        for (int k = 0; k < K; ++k) {
+            const float w = __ldg(wr + k);
+#pragma unroll
+            for (int i = 0; i < FPL; ++i) {
+                const int f = lane + 32 * i;
+                if (f < Fo) acc[i] = fmaf(w, __ldg(yr + k * Fo + f), acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) {
+        const int f = lane + 32 * i;
+        if (f < Fo) out[(int64_t)warp * ldo + f] = acc[i] + (bias ? __ldg(bias + f) : 0.f);
+    }
+}
+
+}  // namespace gnnml3
+
+extern "C" int gnnml3_spmm_projected(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea, int K,
+                                     const float* Y, int64_t ldy, int64_t N, int Fo, const float* bias, float* out, int64_t ldo,
+                                     void* stream_) {
+    GNNML3_REQUIRE(N > 0 && K > 0 && Fo > 0 && Fo <= 256, "spmm_projected: bad shape N=%lld K=%d Fo=%d (Fo <= 256)", (long long)N, K, Fo);
+    GNNML3_REQUIRE(rowptr && col && ea && Y && out, "spmm_projected: NULL pointer");
+    GNNML3_REQUIRE(ldy >= (int64_t)K * Fo && ldo >= Fo, "spmm_projected: leading dimensions too small");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int blocks = (int)((N * 32 + 255) / 256);
+    const int fpl = (Fo + 31) / 32;
+    if (fpl == 1) k_spmm_projected<1><<<blocks, 256, 0, st>>>(rowptr, col, eperm, ea, K, Y, ldy, (int)N, Fo, bias, out, ldo);
+    else if (fpl == 2) k_spmm_projected<2><<<blocks, 256, 0, st>>>(rowptr, col, eperm, ea, K, Y, ldy, (int)N, Fo, bias, out, ldo);
+    else if (fpl <= 4) k_spmm_projected<4><<<blocks, 256, 0, st>>>(rowptr, col, eperm, ea, K, Y, ldy, (int)N, Fo, bias, out, ldo);
+    else k_spmm_projected<8><<<blocks, 256, 0, st>>>(rowptr, col, eperm, ea, K, Y, ldy, (int)N, Fo, bias, out, ldo);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}

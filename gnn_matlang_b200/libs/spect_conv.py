@@ -24,14 +24,21 @@ from torch.nn import Parameter
 from .. import _lib, ops
 from ..graph import get_plan, sorted_edge_attr
 
-_PRECISIONS = {"fp32": _lib.PREC_3XTF32, "3xtf32": _lib.PREC_3XTF32, "tf32": _lib.PREC_TF32}
+_PRECISIONS = {"fp32": _lib.PREC_3XTF32, "3xtf32": _lib.PREC_3XTF32, "tf32": _lib.PREC_TF32, "bf16": _lib.PREC_BF16}
 USE_FUSED = os.environ.get("GNNML3_NO_FUSED", "0") != "1"
 USE_LAYER_API = os.environ.get("GNNML3_NO_LAYER_API", "0") != "1"
 
 
 def _use_fused(precision):
-    """The fused tcgen05 layer kernel implements the FP32-grade (3xTF32) arithmetic only."""
-    return USE_FUSED and precision == _lib.PREC_3XTF32
+    """The fused tcgen05 layer kernels exist for every precision: FP32-grade 3xTF32 in both generations, the flagged
+    single-pass TF32 and BF16 modes in the tensor-memory generation (``_fused_ok`` checks the shape)."""
+    return USE_FUSED
+
+
+def _fused_ok(precision, K, Kstride, F, Nc, Fs=0, self_mode=0, Ns=0):
+    if precision == _lib.PREC_3XTF32:
+        return ops.fused_supported(K, Kstride, F, Nc, Fs, self_mode, Ns)
+    return ops.fused_ts_supported(K, Kstride, F, Nc, Fs, self_mode, Ns)
 
 
 def glorot(tensor):
@@ -78,14 +85,14 @@ class _SpectConvFn(torch.autograd.Function):
         Kw, _, Fo = weight.shape
         K = ea_s.size(1)
         fused = (_use_fused(precision) and N > 0 and plan.E > 0 and (not selfconn or Fi <= 32)
-                 and ops.fused_supported(K, K, Fi, Fo, Fi if selfconn else 0, 2 if selfconn else 0, 0))
+                 and _fused_ok(precision, K, K, Fi, Fo, Fi if selfconn else 0, 2 if selfconn else 0, 0))
         ctx.plan, ctx.selfconn, ctx.precision, ctx.has_bias = plan, selfconn, precision, bias is not None
         ctx.fused = fused
         if fused:
             x = ops.aligned_rows(x)
             out, _ = ops.fused_agg_proj(plan.rowptr, plan.col, None, ea_s, x, weight[:K].reshape(K * Fi, Fo), bias=bias,
                                         S=x if selfconn else None, self_mode=2 if selfconn else 0,
-                                        Bself=weight[K] if selfconn else None, epilogue=0, win=plan.win)
+                                        Bself=weight[K] if selfconn else None, epilogue=0, win=plan.win, precision=precision)
         else:
             H = _aggregate(plan, ea_s, x, Kw)
             if selfconn:
@@ -109,7 +116,7 @@ class _SpectConvFn(torch.autograd.Function):
                     torch.zeros(Fo, device=x.device) if (need_b and ctx.has_bias) else None, None, None, None)
         gout = ops.aligned_rows(gout) if ctx.fused else gout.contiguous()
         fused_dx = (ctx.fused and need_x and (not ctx.selfconn or Fo <= 32)
-                    and ops.fused_supported(K, K, Fo, Fi, Fo if ctx.selfconn else 0, 2 if ctx.selfconn else 0, 0))
+                    and _fused_ok(prec, K, K, Fo, Fi, Fo if ctx.selfconn else 0, 2 if ctx.selfconn else 0, 0))
         G = None
         if fused_dx:
             # dx = sum_k S_k^T gout W_k^T (+ gout W_K^T): the same fused kernel over the transposed CSR; when the weight
@@ -122,7 +129,7 @@ class _SpectConvFn(torch.autograd.Function):
                                        weight[:K].transpose(1, 2).reshape(K * Fo, Fi).contiguous(),
                                        S=gout if ctx.selfconn else None, self_mode=2 if ctx.selfconn else 0,
                                        Bself=weight[K].t().contiguous() if ctx.selfconn else None, epilogue=0, hout=G,
-                                       win=plan.winT)
+                                       win=plan.winT, precision=prec)
             if side:
                 dcat = ops.gemm_tn(x, G, precision=prec)                                          # [Fi, Kw * Fp]
                 dw = dcat.view(Fi, Kw, Fp)[:, :, :Fo].permute(1, 0, 2).contiguous()
@@ -140,13 +147,86 @@ class _SpectConvFn(torch.autograd.Function):
         if need_ea:
             if plan.E == 0:
                 dea = torch.zeros_like(ea_s)
-            elif ctx.fused and ops.fused_sddmm_supported(K, Fi, Fo):
+            elif ctx.fused and ops.fused_sddmm_supported(K, Fi, Fo):      # (FP32-grade in every mode)
                 dea = ops.fused_sddmm(plan.rowptr, plan.col, x, gout, weight[:K].contiguous(), plan.E)
             else:
                 wp = weight[:K].permute(2, 0, 1).reshape(Fo, K * Fi).contiguous()
                 dH = ops.gemm_nn(gout, wp, precision=prec)                   # [N, K*Fi]
                 dea = ops.sddmm_k(plan.rowptr, plan.col, None, x, dH, K, plan.E)
         return dx, dea, dw, db, None, None, None
+
+
+class _SpectConvProjectFirstFn(torch.autograd.Function):
+    """Project-first order of the same layer (north_star: "or alternatively pre-projects and then aggregates"):
+
+        Y = x [W_0 .. W_{K-1}]  ([N, K*Fo], one tensor-core GEMM);   out[t] = sum_{e: dst_e = t} sum_k ea[e, k] Y[src_e, k, :]  (+ bias)
+
+    -- reference libs/spect_conv.py:70-80 with the sum over k moved inside the edge sum.  Backward, atomic-free:
+    dY = [S_0^T gout .. S_{K-1}^T gout] (the K-channel aggregation over the transposed CSR), dx = dY Wcat^T, dWcat = x^T dY,
+    d ea[e, k] = <Y[src_e, k, :], gout[dst_e]> (SDDMM over the transposed CSR)."""
+
+    @staticmethod
+    def forward(ctx, x, ea_s, weight, bias, plan, precision):
+        x, ea_s = x.contiguous(), ea_s.contiguous()
+        K, Fi, Fo = weight.shape
+        wcat = weight.permute(1, 0, 2).reshape(Fi, K * Fo).contiguous()
+        Y = ops.gemm_nn(x, wcat, precision=precision)
+        if plan.E == 0:
+            out = torch.zeros(x.size(0), Fo, device=x.device) + (bias if bias is not None else 0)
+        else:
+            out = ops.spmm_projected(plan.rowptr, plan.col, None, ea_s, Y, Fo, bias)
+        ctx.save_for_backward(x, ea_s, wcat, Y)
+        ctx.plan, ctx.precision, ctx.has_bias, ctx.shape = plan, precision, bias is not None, (K, Fi, Fo)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, ea_s, wcat, Y = ctx.saved_tensors
+        plan, prec = ctx.plan, ctx.precision
+        K, Fi, Fo = ctx.shape
+        gout = gout.contiguous()
+        dY = _aggregate(plan, ea_s, gout, K, transposed=True)                       # [N, K*Fo]
+        dx = ops.gemm_nn(dY, wcat.t().contiguous(), precision=prec) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[2]:
+            dw = ops.gemm_tn(x, dY, precision=prec).view(Fi, K, Fo).permute(1, 0, 2).contiguous()
+        dea = None
+        if ctx.needs_input_grad[1]:
+            dea = (torch.zeros_like(ea_s) if plan.E == 0 else
+                   ops.sddmm_k(plan.rowptrT, plan.colT, plan.permT, gout, Y, K, plan.E))
+        db = ops.colsum(gout) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
+        return dx, dea, dw, db, None, None
+
+
+def project_first_pays(N, E, K, Fi, Fo):
+    """HBM words moved by the aggregation side of the two orders when H = [P_0(x) .. P_{K-1}(x)] / Y = x [W_0 ..] round-trips
+    through HBM (the two-kernel designs): aggregate-first gathers Fi words per support entry and writes + reads H [N, K*Fi];
+    project-first gathers K*Fo words per entry and writes + reads Y [N, K*Fo].  The GEMM flops are the same."""
+    return K * Fo * (E + 2 * N) < Fi * (E + 2 * N * K)
+
+
+class _AggregateFn(torch.autograd.Function):
+    """H = [P_0(x) .. P_{K-1}(x)]  ([N, K*F]) with gradients: dx[s] = sum_{e: src_e = s} sum_k ea[e, k] dH[dst_e, k, :] (the
+    project-first aggregation kernel over the transposed CSR), d ea[e, k] = <x[src_e], dH[dst_e, k, :]> (SDDMM)."""
+
+    @staticmethod
+    def forward(ctx, x, ea_s, plan):
+        x, ea_s = x.contiguous(), ea_s.contiguous()
+        ctx.save_for_backward(x, ea_s)
+        ctx.plan = plan
+        return _aggregate(plan, ea_s, x, ea_s.size(1))
+
+    @staticmethod
+    def backward(ctx, dH):
+        x, ea_s = ctx.saved_tensors
+        plan = ctx.plan
+        dH = dH.contiguous()
+        K, F = ea_s.size(1), x.size(1)
+        if plan.E == 0:
+            return torch.zeros_like(x), torch.zeros_like(ea_s), None
+        dx = ops.spmm_projected(plan.rowptrT, plan.colT, plan.permT, ea_s, dH, F) if ctx.needs_input_grad[0] else None
+        dea = ops.sddmm_k(plan.rowptr, plan.col, None, x, dH, K, plan.E) if ctx.needs_input_grad[1] else None
+        return dx, dea, None
 
 
 class _DepthwiseAggFn(torch.autograd.Function):
@@ -227,8 +307,8 @@ class _ML3LayerFn(torch.autograd.Function):
         K, _, Fo = wconv.shape
         G = 0 if w11 is None else w11.size(0)
         ctx.composite = False
-        if (_use_fused(precision) and USE_LAYER_API and N > 0 and plan.E > 0 and (fused_edge or w1 is None)
-                and ops.ml3layer_supported(K, Fi, Fo, G, fused_edge)):
+        if (_use_fused(precision) and precision == _lib.PREC_3XTF32 and USE_LAYER_API and N > 0 and plan.E > 0
+                and (fused_edge or w1 is None) and ops.ml3layer_supported(K, Fi, Fo, G, fused_edge)):
             # the whole layer in ONE library call (layer_api.cu): same kernels as below, a fraction of the host time
             xa = ops.aligned_rows(x)
             ws4 = tuple(w.contiguous() for w in (w1, w2, w3, w4)) if fused_edge else None
@@ -244,8 +324,8 @@ class _ML3LayerFn(torch.autograd.Function):
         else:
             ea2 = ea_s
         fused = (_use_fused(precision) and N > 0 and plan.E > 0 and (G == 0 or Fi <= 32)
-                 and ops.fused_supported(K, K, Fi, Fo, Fi if G else 0, 1 if G else 0, 2 * G)
-                 and ops.fused_supported(K, K, Fo, Fi, 2 * G, 2 if G else 0, 0))
+                 and _fused_ok(precision, K, K, Fi, Fo, Fi if G else 0, 1 if G else 0, 2 * G)
+                 and _fused_ok(precision, K, K, Fo, Fi, 2 * G, 2 if G else 0, 0))
         ctx.plan, ctx.fused_edge, ctx.precision, ctx.G = plan, fused_edge, precision, G
         ctx.has_bias = bconv is not None
         ctx.fused = fused
@@ -256,7 +336,7 @@ class _ML3LayerFn(torch.autograd.Function):
             bg = torch.cat([b11, b12]) if G > 0 else None
             y, aux = ops.fused_agg_proj(plan.rowptr, plan.col, None, ea2, xa, wconv.view(K * Fi, Fo), bias=bconv,
                                         S=xa if G > 0 else None, self_mode=1 if G > 0 else 0, Bself=wg, bias_s=bg, G=G,
-                                        epilogue=1, win=plan.win)
+                                        epilogue=1, win=plan.win, precision=precision)
             ctx.save_for_backward(xa, ea_s, ea2 if fused_edge else None, y, aux, w1, w2, w3, w4, wconv, w11, w12)
             return y
         H = _aggregate(plan, ea2, x, K)
@@ -317,7 +397,7 @@ class _ML3LayerFn(torch.autograd.Function):
                                        wconv.transpose(1, 2).reshape(K * Fo, Fi).contiguous(),
                                        S=gpre[:, Fo4:Fo4 + 2 * G] if G > 0 else None, self_mode=2 if G > 0 else 0,
                                        Bself=torch.cat([w11, w12], 0).contiguous() if G > 0 else None, epilogue=0,
-                                       win=plan.winT)
+                                       win=plan.winT, precision=prec)
         elif need[0]:
             blocks = [wconv.transpose(1, 2).reshape(K * Fo, Fi)]
             if G > 0:
@@ -372,6 +452,11 @@ class SpectConv(nn.Module):
         self.precision = kwargs.pop('precision', 'fp32')
         if self.precision not in _PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+        # 'auto' (default): the fused aggregate-first kernels where they apply, else whichever order moves fewer HBM words
+        # (project_first_pays); 'aggregate_first' / 'project_first' force one order (measurements)
+        self.order = kwargs.pop('order', 'auto')
+        if self.order not in ('auto', 'aggregate_first', 'project_first'):
+            raise ValueError("order must be 'auto', 'aggregate_first' or 'project_first'")
         super(SpectConv, self).__init__()
         assert K > 0
         self.in_channels = in_channels
@@ -412,6 +497,16 @@ class SpectConv(nn.Module):
                                    % (ea_s.size(1), nk))
             if ea_s.size(1) > nk:          # the reference only reads edge_attr[:, i] for i < K (:76-77)
                 ea_s = ea_s[:, :nk]
+            order = self.order
+            if order == 'auto':
+                Fi, Fo = self.in_channels, self.out_channels
+                fused = _use_fused(prec) and _fused_ok(prec, nk, nk, Fi, Fo, Fi if self.selfconn else 0, 2 if self.selfconn else 0, 0)
+                order = 'project_first' if (not fused and Fo <= 256 and project_first_pays(plan.N, plan.E, nk, Fi, Fo)) else 'aggregate_first'
+            if order == 'project_first' and self.out_channels <= 256:
+                out = _SpectConvProjectFirstFn.apply(x, ea_s, self.weight[:nk], None if self.selfconn else self.bias, plan, prec)
+                if self.selfconn:
+                    out = out + _LinearFn.apply(x, self.weight[nk], self.bias, prec)
+                return out
             return _SpectConvFn.apply(x, ea_s, self.weight, self.bias, plan, self.selfconn, prec)
         nk = self.nsup - (1 if self.selfconn else 0)
         if ea_s.size(1) < nk:
@@ -426,6 +521,73 @@ class SpectConv(nn.Module):
     def __repr__(self):
         return '{}({}, {}, K={})'.format(self.__class__.__name__, self.in_channels, self.out_channels,
                                          self.weight.size(0))
+
+
+class SpectConCatConv(nn.Module):
+    r"""Concatenating variant (reference libs/spect_conv.py:105-165): ``out = [x W_K (if selfconn) || P_0(x) W_0 || .. ||
+    P_{K-1}(x) W_{K-1}] + bias`` with ``bias [K' * out]``; same constructor, parameter names / shapes and ``forward`` signature.
+    One K-channel aggregation kernel builds every ``P_k(x)``, each block is projected by its own tensor-core GEMM."""
+
+    def __init__(self, in_channels, out_channels, K, selfconn=True, bias=True, **kwargs):
+        kwargs.setdefault('aggr', 'add')
+        if kwargs.pop('aggr') != 'add':
+            raise ValueError("SpectConCatConv only implements aggr='add' (the reference's default, :109)")
+        self.precision = kwargs.pop('precision', 'fp32')
+        if self.precision not in _PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+        super(SpectConCatConv, self).__init__()
+        assert K > 0
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.selfconn = selfconn
+        if self.selfconn:
+            K = K + 1
+        self.weight = Parameter(torch.Tensor(K, in_channels, out_channels))
+        if bias:
+            self.bias = Parameter(torch.Tensor(K * out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot(self.weight)
+        zeros(self.bias)
+
+    def forward(self, x, edge_index, edge_attr, edge_weight=None, batch=None, lambda_max=None):
+        _check_inputs(x, edge_index, edge_attr)
+        plan = get_plan(edge_index, x.size(0))
+        ea_s = sorted_edge_attr(edge_attr, plan)
+        prec = _PRECISIONS[self.precision]
+        nk = self.weight.size(0) - (1 if self.selfconn else 0)
+        if ea_s.size(1) < nk:
+            raise RuntimeError("SpectConCatConv: edge_attr has %d channels but the layer was built with K=%d" % (ea_s.size(1), nk))
+        Fi = self.in_channels
+        out = []
+        if self.selfconn:
+            out.append(_LinearFn.apply(x, self.weight[-1], None, prec))
+        H = _AggregateFn.apply(x, ea_s[:, :nk], plan)
+        for i in range(nk):
+            out.append(_LinearFn.apply(H[:, i * Fi:(i + 1) * Fi], self.weight[i], None, prec))
+        out = torch.cat(out, 1)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+    def __repr__(self):
+        return '{}({}, {}, K={})'.format(self.__class__.__name__, self.in_channels, self.out_channels, self.weight.size(0))
+
+
+class EdgeEncoder(torch.nn.Module):
+    """reference libs/spect_conv.py:168-179 (two ReLU linears on the edge features; unused by the reference's scripts)."""
+
+    def __init__(self, emb_dim):
+        super(EdgeEncoder, self).__init__()
+        self.fc1 = torch.nn.Linear(emb_dim[0], emb_dim[1])
+        self.fc2 = torch.nn.Linear(emb_dim[1], emb_dim[2])
+
+    def forward(self, edge_attr):
+        h = torch.relu(_LinearFn.apply(edge_attr, self.fc1.weight.t(), self.fc1.bias, _lib.PREC_3XTF32))
+        return torch.relu(_LinearFn.apply(h, self.fc2.weight.t(), self.fc2.bias, _lib.PREC_3XTF32))
 
 
 class ML3Layer(torch.nn.Module):

@@ -155,6 +155,23 @@ def spmm_k(rowptr, col, eperm, ea, x, out=None):
     return out
 
 
+def spmm_projected(rowptr, col, eperm, ea, Y, Fo, bias=None):
+    """out[t, f] = sum_{p in row t} sum_k ea[e(p), k] * Y[col[p], k*Fo + f] (+ bias)  -> [N, Fo]  (project-first SpectConv)"""
+    lib = _lib.load()
+    Y = _rows(Y, "Y")
+    ea = _f32c(ea, "edge_attr")
+    N, K = Y.size(0), ea.size(1)
+    out = torch.empty(N, Fo, dtype=torch.float32, device=Y.device)
+    if N == 0:
+        return out
+    if bias is not None:
+        bias = _f32c(bias, "bias")
+    with _on(Y.device):
+        _lib.check(lib.gnnml3_spmm_projected(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(ea), K, _lib.ptr(Y), _ld(Y), N, Fo,
+                                             _lib.ptr(bias), _lib.ptr(out), _ld(out), _lib.stream_ptr()), "gnnml3_spmm_projected")
+    return out
+
+
 def sddmm_k(rowptr, col, eperm, x, g, K, E):
     """dea[e(p), k] = <x[col[p]], g[t, k*F:(k+1)*F]>  -> [E, K]"""
     lib = _lib.load()
@@ -201,6 +218,7 @@ def gemm_nn(A, B, bias=None, precision=_lib.PREC_3XTF32, epilogue=_lib.EPI_NONE,
     """C = A @ B (+ bias) (+ relu) on the tensor cores; A [M,Kc], B [Kc,Nc].  FP32-grade (3xTF32) requests with
     16-byte aligned rows run on tcgen05/TMEM; everything else on the mma.sync kernel."""
     lib = _lib.load()
+    precision = min(int(precision), _lib.PREC_TF32)
     A = _rows(A, "A")
     B = _f32c(B, "B")
     M, Kc = A.shape
@@ -225,6 +243,7 @@ def gemm_nn(A, B, bias=None, precision=_lib.PREC_3XTF32, epilogue=_lib.EPI_NONE,
 def gemm_tn(A, B, precision=_lib.PREC_3XTF32):
     """C = A^T @ B; A [M,Ka], B [M,Nb] -> [Ka,Nb]; deterministic split over M."""
     lib = _lib.load()
+    precision = min(int(precision), _lib.PREC_TF32)
     A = _rows(A, "A")
     B = _rows(B, "B")
     M, Ka = A.shape
@@ -341,8 +360,13 @@ def fused_supported(K, Kstride, F, Nc, Fs=0, self_mode=0, Ns=0):
     return bool(_lib.load().gnnml3_fused_supported(int(K), int(Kstride), int(F), int(Nc), int(Fs), int(self_mode), int(Ns)))
 
 
+def fused_ts_supported(K, Kstride, F, Nc, Fs=0, self_mode=0, Ns=0):
+    """Shape covered by the tensor-memory generation of the fused kernel (the only one with the TF32 / BF16 modes)."""
+    return bool(_lib.load().gnnml3_fused_ts_supported(int(K), int(Kstride), int(F), int(Nc), int(Fs), int(self_mode), int(Ns)))
+
+
 def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mode=0, Bself=None, bias_s=None, G=0,
-                   epilogue=0, hout=None, win=None):
+                   epilogue=0, hout=None, win=None, precision=_lib.PREC_3XTF32):
     """Fused aggregate + project (gnnml3_fused_agg_proj).  x [*, F] and S [N, Fs] must satisfy ``aligned_rows``.
     epilogue 0 -> out [N, Nc];  epilogue 1 -> (y [N, Nc + G], aux [N, 2G]) = the ML3Layer node branch."""
     lib = _lib.load()
@@ -381,7 +405,7 @@ def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mod
             _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(ea), K, K, _lib.ptr(x), _ld(x), F,
             _lib.ptr(S) if self_mode else None, _ld(S) if self_mode else 0, Fs, self_mode, _lib.ptr(Bmain), _ld(Bmain),
             _lib.ptr(Bself) if self_mode else None, _ld(Bself) if self_mode else 0, Ns, _lib.ptr(bias), _lib.ptr(bias_s),
-            N, Nc, _lib.ptr(out), ldo, _lib.ptr(aux), 2 * G, G, epilogue, _lib.ptr(hout), _ld(hout) if hout is not None else 0,
+            N, Nc, _lib.ptr(out), ldo, _lib.ptr(aux), 2 * G, G, epilogue | _lib.FUSED_FLAGS[precision], _lib.ptr(hout), _ld(hout) if hout is not None else 0,
             _lib.ptr(win), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
             "gnnml3_fused_agg_proj")
     return out, aux
@@ -562,7 +586,7 @@ def _instrument(name, fn):
     return wrapped
 
 
-for _n in ("csr_build", "gather_rows", "scatter_rows", "spmm_k", "sddmm_k", "gemm_nn_tc", "gemm_nn", "gemm_tn", "colsum", "edge_mlp_fwd",
+for _n in ("csr_build", "gather_rows", "scatter_rows", "spmm_k", "spmm_projected", "sddmm_k", "gemm_nn_tc", "gemm_nn", "gemm_tn", "colsum", "edge_mlp_fwd",
            "edge_mlp_bwd", "ml3_act_fwd", "ml3_act_bwd", "ml3_act_bwd_y", "fused_agg_proj", "fused_sddmm", "ml3layer_forward", "ml3layer_backward", "segment_pool_fwd",
            "segment_pool_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

@@ -47,6 +47,12 @@ extern "C" {
 #define GNNML3_PREC_3XTF32 0
 #define GNNML3_PREC_TF32 1
 
+/* precision flags OR-ed into the `epilogue` argument of gnnml3_fused_agg_proj (tensor-memory kernel only): one tensor-core
+ * product per k-step on TF32-truncated / BF16-rounded inputs instead of the FP32-grade 3xTF32 triple; FP32 accumulation.
+ * Stated tolerances (tests/test_gpu_fused.py): TF32 2e-3, BF16 2e-2 of the result's scale. */
+#define GNNML3_FUSED_TF32 0x100
+#define GNNML3_FUSED_BF16 0x200
+
 /* epilogues of gnnml3_gemm_nn */
 #define GNNML3_EPI_NONE 0
 #define GNNML3_EPI_RELU 1
@@ -82,6 +88,12 @@ GNNML3_API int gnnml3_scatter_rows(const float* in, const int32_t* perm, int64_t
  * --------------------------------------------------------------------------------------------------- */
 GNNML3_API int gnnml3_spmm_k(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea,
                   const float* x, int64_t ldx, int64_t N, int K, int F, float* out, int64_t ldo, void* stream);
+
+/* Project-first order of SpectConv (the sum over supports moved inside the edge sum; libs/spect_conv.py:70-80):
+ *   out[t, f] = sum_{p in row t} sum_k ea[e(p), k] * Y[col[p], k*Fo + f]  (+ bias[f]),   Y = x [W_0 .. W_{K-1}]  ([N, K*Fo])
+ * Gathers K*Fo floats per support entry instead of F_in: chosen when the layer narrows. */
+GNNML3_API int gnnml3_spmm_projected(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* ea, int K,
+                          const float* Y, int64_t ldy, int64_t N, int Fo, const float* bias, float* out, int64_t ldo, void* stream);
 
 /* d ea[e(p), k] = < x[col[p], :], g[t, k*F : (k+1)*F] >  for every edge p of every row t (SDDMM). */
 GNNML3_API int gnnml3_sddmm_k(const int32_t* rowptr, const int32_t* col, const int32_t* eperm, const float* x, int64_t ldx,

@@ -119,6 +119,21 @@ def spectconv_forward(x, edge_index, edge_attr, weight, bias=None, selfconn=Fals
     return out
 
 
+def spectconcatconv_forward(x, edge_index, edge_attr, weight, bias=None, selfconn=True):
+    """libs/spect_conv.py:137-158: ``[x W_last (if selfconn) || P_0(x) W_0 || .. ] + bias``  (bias has K' * out entries)."""
+    out = []
+    enditr = weight.size(0)
+    if selfconn:
+        out.append(torch.matmul(x, weight[-1]))
+        enditr -= 1
+    for i in range(enditr):
+        out.append(torch.matmul(propagate_add(x, edge_index, edge_attr[:, i]), weight[i]))
+    out = torch.cat(out, 1)
+    if bias is not None:
+        out = out + bias
+    return out
+
+
 def spectconv_forward_dense(x, edge_index, edge_attr, weight, bias=None):
     """Independent dense statement of the default branch, after libs/layers_tf.py:222-245
     (``sum_k (S_k @ X) @ W_k`` with dense supports): S_k[t, s] = sum of edge_attr[e, k] over edges s->t."""

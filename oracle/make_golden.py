@@ -255,6 +255,35 @@ def main():
     for k, v in model.state_dict().items():
         blob["p/" + k] = v.numpy()
     np.savez_compressed(os.path.join(OUT, "graph8c_model.npz"), **blob)
+    # ------------------------------------------------------------------ SpectConCatConv fixtures (libs/spect_conv.py:105-165)
+    # (own file and own seed: the fixtures above keep their RNG stream and regenerate bit-identically)
+    torch.manual_seed(1)
+    blob, meta = {}, []
+    for c in [dict(name="concat_selfconn", N=40, E=300, K=3, Fi=5, Fo=7, kw=dict(selfconn=True)),
+              dict(name="concat_noself", N=33, E=250, K=4, Fi=6, Fo=3, kw=dict(selfconn=False)),
+              dict(name="concat_nobias", N=20, E=120, K=2, Fi=8, Fo=8, kw=dict(selfconn=True, bias=False)),
+              dict(name="concat_wide", N=64, E=600, K=6, Fi=40, Fo=12, kw=dict(selfconn=False))]:
+        x, ei, ea = rand_graph(c["N"], c["E"], c["K"], c["Fi"])
+        x.requires_grad_(True)
+        ea.requires_grad_(True)
+        m = ref_conv.SpectConCatConv(c["Fi"], c["Fo"], c["K"], **c["kw"])
+        if m.bias is not None:
+            with torch.no_grad():
+                m.bias.normal_(0, 0.3)
+        out = m(x, ei, ea)
+        gout = torch.randn_like(out)
+        out.backward(gout)
+        n = c["name"]
+        blob[n + "/x"], blob[n + "/ei"], blob[n + "/ea"] = x.detach().numpy(), ei.numpy(), ea.detach().numpy()
+        blob[n + "/out"], blob[n + "/gout"] = out.detach().numpy(), gout.numpy()
+        blob[n + "/gx"], blob[n + "/gea"] = x.grad.numpy(), ea.grad.numpy()
+        for pn, p in m.named_parameters():
+            blob[n + "/p/" + pn] = p.detach().numpy()
+            blob[n + "/g/" + pn] = p.grad.numpy()
+        meta.append(dict(name=n, kind="concat", Fi=c["Fi"], Fo=c["Fo"], K=c["K"], kw=c["kw"], repr=repr(m)))
+    blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "spect_concat.npz"), **blob)
+
     print("params:", sum(p.numel() for p in model.parameters()))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -260,3 +260,85 @@ def test_act_bwd_y_layout_and_sums():
     assert_close(gpre[:, Fo4:Fo4 + 2 * G], pr.grad[:, Fo:], name="gates")
     assert float(gpre[:, Fo:Fo4].abs().max()) == 0.0
     assert_close(csum, pr.grad.sum(0), name="bias sums")
+
+
+@pytest.mark.parametrize("precision,rtol", [("tf32", 2e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("N,deg,K,F,Nc,G", [(3000, 6, 8, 32, 30, 2), (1000, 5, 6, 2, 32, 16), (2000, 6, 12, 32, 16, 16), (1500, 4, 8, 30, 48, 0)])
+def test_fused_flagged_precisions(N, deg, K, F, Nc, G, precision, rtol):
+    """north_star "(TF32, or bf16 when flagged)": the tensor-memory kernel with ONE tensor-core product per k-step on TF32-
+    truncated / BF16-rounded inputs, FP32 accumulation.  Stated tolerances relative to the result's scale: TF32 2e-3 (10-bit
+    mantissa, inputs truncated), BF16 2e-2 (8-bit mantissa, 256-term contractions)."""
+    from gnn_matlang_b200 import _lib, ops
+    prec = {"tf32": _lib.PREC_TF32, "bf16": _lib.PREC_BF16}[precision]
+    ei, g = _graph(N, deg, N + K)
+    E = ei.size(1)
+    x = torch.randn(N, F, generator=g)
+    ea = torch.randn(E, K, generator=g)
+    W = torch.randn(K, F, Nc, generator=g) / np.sqrt(K * F)
+    bias = torch.randn(Nc, generator=g) * 0.3
+    d = dev()
+    plan = ops.csr_build(ei.to(d), N)
+    ea_s = ea.to(d)[plan["perm"].long()].contiguous()
+    xa = ops.aligned_rows(x.to(d))
+    ref = _ref_main(x, ei, ea, W, bias)
+    before = ops.fused_path_counts()
+    if G > 0:
+        w11 = torch.randn(G, F, generator=g) / np.sqrt(F)
+        w12 = torch.randn(G, F, generator=g) / np.sqrt(F)
+        b11, b12 = torch.randn(G, generator=g) * 0.2, torch.randn(G, generator=g) * 0.2
+        wg = torch.cat([w11.t(), w12.t()], 1).contiguous().to(d)
+        y, aux = ops.fused_agg_proj(plan["rowptr"], plan["col"], None, ea_s, xa, W.view(K * F, Nc).to(d), bias=bias.to(d), S=xa, self_mode=1,
+                                    Bself=wg, bias_s=torch.cat([b11, b12]).to(d), G=G, epilogue=1, win=plan["win"], precision=prec)
+        t1 = torch.tanh(x.double() @ w11.double().t() + b11.double())
+        t2 = torch.tanh(x.double() @ w12.double().t() + b12.double())
+        assert_close(y[:, :Nc], torch.relu(ref), rtol=rtol, name="relu(conv) " + precision)
+        assert_close(y[:, Nc:], t1 * t2, rtol=rtol, name="gate " + precision)
+        assert_close(aux, torch.cat([t1, t2], 1), rtol=rtol, name="aux " + precision)
+        err = (y[:, :Nc].cpu().double() - torch.relu(ref)).abs().max() / ref.abs().max()
+    else:
+        out, _ = ops.fused_agg_proj(plan["rowptr"], plan["col"], None, ea_s, xa, W.view(K * F, Nc).to(d), bias=bias.to(d), epilogue=0,
+                                    win=plan["win"], precision=prec)
+        assert_close(out, ref, rtol=rtol, name="conv " + precision)
+        err = (out.cpu().double() - ref).abs().max() / ref.abs().max()
+    assert ops.fused_path_counts()[0] == before[0] + 1
+    # the flagged modes must really be reduced precision (a silent fall-through to 3xTF32 would sit at ~1e-7)
+    assert float(err) > 1e-5, "suspiciously exact for %s: %.2e" % (precision, float(err))
+
+
+@pytest.mark.parametrize("precision,rtol", [("tf32", 5e-3), ("bf16", 5e-2)])
+def test_ml3layer_module_in_flagged_precision(precision, rtol):
+    """ML3Layer(precision=...) forward + backward through the fused tensor-memory kernels in the flagged modes vs the oracle."""
+    from gnn_matlang_b200.libs.spect_conv import ML3Layer
+    from oracle import gnnml3_oracle as O
+    g = torch.Generator().manual_seed(3)
+    N, deg, K = 2000, 5, 8
+    ei, _ = _graph(N, deg, 5)
+    x = torch.randn(N, 32, generator=g)
+    ea = torch.randn(ei.size(1), K, generator=g)
+    torch.manual_seed(1)
+    ref = O.OracleML3Layer(True, K, K, 32, 30, 2)
+    lay = ML3Layer(True, K, K, 32, 30, 2, precision=precision)
+    lay.load_state_dict(ref.state_dict())
+    lay = lay.to(dev())
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, ei, ea)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    xd = x.to(dev()).requires_grad_(True)
+    y = lay(xd, ei.to(dev()), ea.to(dev()))
+    y.backward(gy.to(dev()))
+    assert_close(y, yr, rtol=rtol, name="layer out")
+
+    def close_in_norm(a, ref, name):
+        """Reduced precision flips the ReLU mask of pre-activations within ~rtol of zero, which changes single gradient entries
+        by O(1): gradients are held to the tolerance in the Frobenius norm and entry-wise for at least 99 % of the entries."""
+        a, ref = a.detach().cpu().double(), ref.detach().cpu().double()
+        rel = float((a - ref).norm() / ref.norm())
+        frac_bad = float(((a - ref).abs() > rtol * ref.abs() + rtol * ref.abs().max()).double().mean())
+        assert rel <= 4 * rtol, "%s: relative Frobenius error %.3e" % (name, rel)
+        if ref.numel() >= 10000:          # (small weight tensors are sums over all nodes: the norm bound is the meaningful one)
+            assert frac_bad <= 0.01, "%s: %.2f %% entries off" % (name, 100 * frac_bad)
+
+    close_in_norm(xd.grad, xr.grad, "dx")
+    for (k, p), (_, pr) in zip(lay.named_parameters(), ref.named_parameters()):
+        close_in_norm(p.grad, pr.grad, "grad " + k)

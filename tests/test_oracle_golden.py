@@ -189,3 +189,23 @@ def test_spectral_design_invariants():
         assert np.array_equal(ea2[:, nf], (ei2[0] == ei2[1]).astype(np.float32))
         if c["kw"].get("addadj") and c["kw"]["recfield"] == 1:
             assert np.array_equal(ea2[:, nf + 1], (ei2[0] != ei2[1]).astype(np.float32))
+
+
+CC_Z, CC_META = load_npz("spect_concat.npz")
+
+
+@pytest.mark.parametrize("case", CC_META, ids=lambda c: c["name"])
+def test_spectconcatconv_matches_reference(case):
+    """oracle restatement of libs/spect_conv.py:105-165 against the fixture generated by the unmodified reference"""
+    n = case["name"]
+    p = {k: v.requires_grad_(True) for k, v in _params(CC_Z, n).items()}
+    x = torch.tensor(CC_Z[n + "/x"], requires_grad=True)
+    ea = torch.tensor(CC_Z[n + "/ea"], requires_grad=True)
+    ei = torch.tensor(CC_Z[n + "/ei"])
+    out = O.spectconcatconv_forward(x, ei, ea, p["weight"], p.get("bias"), selfconn=case["kw"].get("selfconn", True))
+    np.testing.assert_array_equal(out.detach().numpy(), CC_Z[n + "/out"])      # same ops, same order: bit-equal
+    out.backward(torch.tensor(CC_Z[n + "/gout"]))
+    np.testing.assert_allclose(x.grad.numpy(), CC_Z[n + "/gx"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ea.grad.numpy(), CC_Z[n + "/gea"], rtol=1e-6, atol=1e-6)
+    for k, v in p.items():
+        np.testing.assert_allclose(v.grad.numpy(), CC_Z[n + "/g/" + k], rtol=1e-6, atol=1e-6)
