@@ -192,6 +192,45 @@ __global__ void __launch_bounds__(256) k_segment_pool_bwd(const float* __restric
     for (int n = n0; n < n1; ++n) gx[(int64_t)n * ldx + f] = g;
 }
 
+// PyG global_max_pool (enzymes.py:340,384: read-out of the GNNML3 variants): per-graph maximum over the node range and the
+// node that attains it (first one on ties, as a sequential scan would); an empty graph gives 0 / -1 (torch_scatter's fill).
+__global__ void __launch_bounds__(256) k_segment_max_fwd(const float* __restrict__ x, int64_t ldx, const int* __restrict__ gptr,
+                                                         int B, int F, float* __restrict__ out, int* __restrict__ arg) {
+    const int lane = threadIdx.x & 31;
+    const int chunks = (F + 31) / 32;
+    const int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)B * chunks) return;
+    const int b = (int)(w / chunks), f = (int)(w % chunks) * 32 + lane;
+    const int n0 = __ldg(gptr + b), n1 = __ldg(gptr + b + 1);
+    if (f >= F) return;
+    float m = 0.f;
+    int a = -1;
+    for (int n = n0; n < n1; ++n) {
+        const float v = __ldg(x + (int64_t)n * ldx + f);
+        if (a < 0 || v > m) {
+            m = v;
+            a = n;
+        }
+    }
+    out[(int64_t)b * F + f] = m;
+    arg[(int64_t)b * F + f] = a;
+}
+
+// gx[n, f] = gout[b, f] if n == arg[b, f] else 0   (every element of gx written exactly once: no atomics, no pre-zeroing)
+__global__ void __launch_bounds__(256) k_segment_max_bwd(const float* __restrict__ gout, const int* __restrict__ arg,
+                                                         const int* __restrict__ gptr, int B, int F, float* __restrict__ gx, int64_t ldx) {
+    const int lane = threadIdx.x & 31;
+    const int chunks = (F + 31) / 32;
+    const int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)B * chunks) return;
+    const int b = (int)(w / chunks), f = (int)(w % chunks) * 32 + lane;
+    const int n0 = __ldg(gptr + b), n1 = __ldg(gptr + b + 1);
+    if (f >= F) return;
+    const float g = __ldg(gout + (int64_t)b * F + f);
+    const int a = __ldg(arg + (int64_t)b * F + f);
+    for (int n = n0; n < n1; ++n) gx[(int64_t)n * ldx + f] = n == a ? g : 0.f;
+}
+
 static int ew_grid(int64_t n) {
     int64_t b = (n + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * 16;
@@ -250,6 +289,28 @@ extern "C" int gnnml3_segment_pool_fwd(const float* x, int64_t ldx, const int32_
     GNNML3_REQUIRE(x && graph_ptr && out && ldx >= F, "segment_pool_fwd: bad arguments");
     const int64_t warps = (int64_t)B * ((F + 31) / 32);
     k_segment_pool_fwd<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(x, ldx, graph_ptr, B, F, mean, out);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+extern "C" int gnnml3_segment_max_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int B, int F, float* out, int32_t* arg,
+                                      void* stream_) {
+    GNNML3_REQUIRE(B >= 0 && F > 0, "segment_max_fwd: bad shape");
+    if (B == 0) return GNNML3_OK;
+    GNNML3_REQUIRE(x && graph_ptr && out && arg && ldx >= F, "segment_max_fwd: bad arguments");
+    const int64_t warps = (int64_t)B * ((F + 31) / 32);
+    k_segment_max_fwd<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(x, ldx, graph_ptr, B, F, out, arg);
+    GNNML3_LAUNCH_CHECK();
+    return GNNML3_OK;
+}
+
+extern "C" int gnnml3_segment_max_bwd(const float* gout, const int32_t* arg, const int32_t* graph_ptr, int B, int F, float* gx,
+                                      int64_t ldx, void* stream_) {
+    GNNML3_REQUIRE(B >= 0 && F > 0, "segment_max_bwd: bad shape");
+    if (B == 0) return GNNML3_OK;
+    GNNML3_REQUIRE(gout && arg && graph_ptr && gx && ldx >= F, "segment_max_bwd: bad arguments");
+    const int64_t warps = (int64_t)B * ((F + 31) / 32);
+    k_segment_max_bwd<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(gout, arg, graph_ptr, B, F, gx, ldx);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }

@@ -549,6 +549,29 @@ def segment_pool_bwd(gout, graph_ptr, mean, N):
     return gx
 
 
+def segment_max_fwd(x, graph_ptr):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    B, F = graph_ptr.numel() - 1, x.size(1)
+    out = torch.empty(B, F, dtype=torch.float32, device=x.device)
+    arg = torch.empty(B, F, dtype=torch.int32, device=x.device)
+    with _on(x.device):
+        _lib.check(lib.gnnml3_segment_max_fwd(_lib.ptr(x), _ld(x), _lib.ptr(graph_ptr), B, F, _lib.ptr(out), _lib.ptr(arg),
+                                              _lib.stream_ptr()), "gnnml3_segment_max_fwd")
+    return out, arg
+
+
+def segment_max_bwd(gout, arg, graph_ptr, N):
+    lib = _lib.load()
+    gout = _f32c(gout, "gout")
+    B, F = gout.shape
+    gx = torch.empty(N, F, dtype=torch.float32, device=gout.device)
+    with _on(gout.device):
+        _lib.check(lib.gnnml3_segment_max_bwd(_lib.ptr(gout), _lib.ptr(arg), _lib.ptr(graph_ptr), B, F, _lib.ptr(gx), _ld(gx),
+                                              _lib.stream_ptr()), "gnnml3_segment_max_bwd")
+    return gx
+
+
 # --------------------------------------------------------------------------------------------------
 # optional per-call device timing (CUDA events on the launching stream) used by bench.py
 # --------------------------------------------------------------------------------------------------

@@ -19,10 +19,23 @@ class _SegmentPoolFn(torch.autograd.Function):
         return ops.segment_pool_bwd(g.contiguous(), ctx.graph_ptr, ctx.mean, ctx.N), None, None
 
 
+class _SegmentMaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, graph_ptr):
+        out, arg = ops.segment_max_fwd(x, graph_ptr)
+        ctx.graph_ptr, ctx.N = graph_ptr, x.size(0)
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.segment_max_bwd(g.contiguous(), ctx.saved_tensors[0], ctx.graph_ptr, ctx.N), None
+
+
 def graph_ptr_from_batch(batch, size=None):
     """``batch`` [N] (sorted graph id per node) -> int32 ``graph_ptr`` [B+1]; cached on the tensor object."""
     cached = getattr(batch, "_gnnml3_ptr", None)
-    if cached is not None and cached[0] == batch._version:
+    if cached is not None and cached[0] == batch._version and (size is None or cached[1].numel() == int(size) + 1):
         return cached[1]
     if not batch.is_cuda:
         raise RuntimeError("gnn_matlang_b200: batch must be a CUDA tensor (no CPU fallback)")
@@ -43,3 +56,8 @@ def global_add_pool(x, batch, size=None):
 
 def global_mean_pool(x, batch, size=None):
     return _SegmentPoolFn.apply(x, graph_ptr_from_batch(batch, size), True)
+
+
+def global_max_pool(x, batch, size=None):
+    """PyG ``global_max_pool`` (enzymes.py:340,384; ptc.py): per-graph maximum, gradient to the node that attains it."""
+    return _SegmentMaxFn.apply(x, graph_ptr_from_batch(batch, size))

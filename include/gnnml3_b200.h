@@ -246,6 +246,12 @@ GNNML3_API int gnnml3_segment_pool_fwd(const float* x, int64_t ldx, const int32_
                             float* out, void* stream);
 GNNML3_API int gnnml3_segment_pool_bwd(const float* gout, const int32_t* graph_ptr, int B, int F, int mean, float* gx,
                             int64_t ldx, void* stream);
+/* PyG global_max_pool (read-out of the GNNML3 variants, enzymes.py:340,384): out [B,F] = per-graph maximum, arg [B,F] = the
+ * node attaining it (first on ties; -1 and 0 for an empty graph); bwd routes gout to that node and writes zeros elsewhere. */
+GNNML3_API int gnnml3_segment_max_fwd(const float* x, int64_t ldx, const int32_t* graph_ptr, int B, int F, float* out, int32_t* arg,
+                           void* stream);
+GNNML3_API int gnnml3_segment_max_bwd(const float* gout, const int32_t* arg, const int32_t* graph_ptr, int B, int F, float* gx,
+                           int64_t ldx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * SpectralDesign (libs/utils.py:525-610), batched: one thread block per graph, FP64 Jacobi eigensolver.

@@ -51,6 +51,56 @@ def global_mean_pool(x, batch, num_graphs):
     return s / cnt.view(-1, 1)
 
 
+def global_max_pool(x, batch, num_graphs):
+    """PyG global_max_pool (torch_scatter 'max', third-party -- restated): per-graph maximum; an empty graph gives 0."""
+    out = torch.zeros(num_graphs, x.size(1), dtype=x.dtype)
+    for b in range(num_graphs):
+        m = batch == b
+        if bool(m.any()):
+            out[b] = x[m].max(0).values
+    return out
+
+
+class OracleGNNML3Variant(torch.nn.Module):
+    """The GNNML3 variants of the TU-dataset scripts: ``enzymes`` (enzymes.py:345-386: 4 x ML3Layer(64||0, learnedge=False),
+    dropout 0.1 before every layer, add||max read-out, BatchNorm1d, log_softmax(fc2)) and ``mutag`` (mutag.py:268-307:
+    3 x ML3Layer(24||24, learnedge=False) + BatchNorm1d each, mean read-out, fc2(relu(fc1)))."""
+
+    def __init__(self, config, ne, ninp):
+        super().__init__()
+        self.config = config
+        if config == "enzymes":
+            nout1, nout2, nl = 64, 0, 4
+        else:
+            nout1, nout2, nl = 24, 24, 3
+        nin = nout1 + nout2
+        self.nl = nl
+        for l in range(nl):
+            setattr(self, "conv%d" % (l + 1), OracleML3Layer(False, ne, ne, ninp if l == 0 else nin, nout1, nout2))
+        if config == "enzymes":
+            self.bn4 = torch.nn.BatchNorm1d(2 * nin)
+            self.fc2 = torch.nn.Linear(2 * nin, 6)
+        else:
+            for l in range(nl):
+                setattr(self, "bn%d" % (l + 1), torch.nn.BatchNorm1d(nin))
+            self.fc1 = torch.nn.Linear(nin, 32)
+            self.fc2 = torch.nn.Linear(32, 1)
+
+    def forward(self, b):
+        x, ei, ea = b["x"], b["edge_index2"], b["edge_attr2"]
+        for l in range(self.nl):
+            if self.config == "enzymes":
+                x = F.dropout(x, p=0.1, training=self.training)
+            x = getattr(self, "conv%d" % (l + 1))(x, ei, ea)
+            if self.config == "mutag":
+                x = getattr(self, "bn%d" % (l + 1))(x)
+        if self.config == "enzymes":
+            x = torch.cat([global_add_pool(x, b["batch"], b["num_graphs"]), global_max_pool(x, b["batch"], b["num_graphs"])], 1)
+            return F.log_softmax(self.fc2(self.bn4(x)), dim=1)
+        x = global_mean_pool(x, b["batch"], b["num_graphs"])
+        return self.fc2(F.relu(self.fc1(x)))
+
+
 def collate(graphs):
     """PyG ``Batch.from_data_list`` restricted to the attributes GNNML3 reads.
 

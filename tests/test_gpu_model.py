@@ -184,3 +184,64 @@ def test_model_training_step_matches_oracle(cfg):
         msgs.append("seed %d: node margin %.1e edge margin %.1e: %s" % (seed, node_m, edge_m, msg[:200]))
         assert node_m < 1e-5 or edge_m < 1e-6, "gradient mismatch without a ReLU kink nearby: " + msgs[-1]
     pytest.fail("gradients differ on every batch:\n" + "\n".join(msgs))
+
+
+def test_global_max_pool_matches_oracle():
+    from gnn_matlang_b200.pool import global_max_pool
+    g = torch.Generator().manual_seed(3)
+    sizes = [5, 1, 0, 17, 3]                                    # an empty graph in the middle
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    x = torch.randn(sum(sizes), 37, generator=g)
+    x[7] = x[6]                                                 # a tie inside graph 3
+    xg = x.to(dev()).requires_grad_(True)
+    out = global_max_pool(xg, batch.to(dev()), len(sizes))
+    ref_x = x.clone().requires_grad_(True)
+    ref = O.global_max_pool(ref_x, batch, len(sizes))
+    assert torch.equal(out.cpu(), ref.detach())                 # a maximum is exact
+    gout = torch.randn(len(sizes), 37, generator=g)
+    out.backward(gout.to(dev()))
+    ref.backward(gout)
+    # the gradient goes to ONE arg-max node; on the tie torch's max also picks one: compare the per-graph column sums and the
+    # untied rows
+    keep = torch.ones(sum(sizes), dtype=torch.bool)
+    keep[6:8] = False
+    assert torch.equal(xg.grad.cpu()[keep], ref_x.grad[keep])
+    assert torch.allclose(xg.grad.cpu()[6:8].sum(0), ref_x.grad[6:8].sum(0))
+
+
+@pytest.mark.parametrize("cfg,train", [("mutag", True), ("enzymes", False)])
+def test_gnnml3_variants_match_oracle(cfg, train):
+    """The GNNML3 variants with unlearned edge features, BatchNorm, dropout and concatenated read-outs (enzymes.py:345-386,
+    mutag.py:268-307).  mutag in training mode (BatchNorm batch statistics, no dropout in that script); enzymes in eval mode
+    (dropout is random in training) with non-trivial BatchNorm running statistics."""
+    from gnn_matlang_b200.batch import collate
+    from gnn_matlang_b200.models import GNNML3
+    g = torch.Generator().manual_seed(77)
+    graphs = _random_graphs("exp", 24, g)
+    ne, ninp = graphs[0]["edge_attr2"].shape[1], graphs[0]["x"].shape[1]
+    torch.manual_seed(5)
+    ref = O.OracleGNNML3Variant(cfg, ne, ninp)
+    model = GNNML3(cfg, ne, ninp)
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    if cfg == "enzymes":
+        with torch.no_grad():
+            ref.bn4.running_mean.normal_(0, 1.0)
+            ref.bn4.running_var.uniform_(0.5, 2.0)
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev())
+    ref.train(train)
+    model.train(train)
+    ob = O.collate(graphs)
+    out_r = ref(ob)
+    out = model(collate(graphs).to(dev()))
+    assert_close(out, out_r, rtol=2e-5, name=cfg + " out")
+    gout = torch.randn(out_r.shape, generator=g)
+    out_r.backward(gout)
+    out.backward(gout.to(dev()))
+    bad = []
+    for (k, p), (_, pr) in zip(model.named_parameters(), ref.named_parameters()):
+        try:
+            assert_close(p.grad, pr.grad, rtol=2e-4, name="grad " + k)
+        except AssertionError as e:
+            bad.append(str(e)[:120])
+    assert len(bad) <= 1, bad        # (one tensor may sit on a ReLU / arg-max kink, see _kink_margin)
