@@ -437,6 +437,19 @@ def fused_path_counts(reset=False):
     return int(buf[0]), int(buf[1])
 
 
+def edge_mlp_path_counts(reset=False):
+    """(calls served by the tcgen05 edge-MLP kernels, calls served by the FP32-FMA kernels) since the last reset."""
+    import ctypes
+    buf = (ctypes.c_longlong * 2)()
+    _lib.load().gnnml3_edge_mlp_path_counts(buf, int(bool(reset)))
+    return int(buf[0]), int(buf[1])
+
+
+def edge_mlp_set_tc(enable):
+    """Select the tcgen05 (True, default) or the FP32-FMA (False) generation of the edge-MLP kernels; returns the old setting."""
+    return bool(_lib.load().gnnml3_edge_mlp_set_tc(int(bool(enable))))
+
+
 def fused_side_output_ok():
     """The aggregate side output (``hout``) of fused_agg_proj exists in the default aggregator mode only."""
     return _lib.load().gnnml3_fused_set_mode(-1) == 0

@@ -125,6 +125,11 @@ GNNML3_API int gnnml3_colsum(const float* A, int64_t lda, int64_t M, int Nc, flo
  * bwd recomputes the activations; dea (nullable) receives d ea at e(p); dw1..dw4 are overwritten.
  * --------------------------------------------------------------------------------------------------- */
 GNNML3_API int gnnml3_edge_mlp_supported(int K, int Kout);
+/* Two generations of the same contract: tcgen05 (default: edges on the tensor-memory lanes, weights as shared-memory planes,
+ * 3xTF32 FP32-grade) and the FP32-FMA kernels of round 1.  set_tc(0/1) selects (returns the old value; GNNML3_EDGE_TC=0 in the
+ * environment does the same at load time); path_counts reports {tensor-core, CUDA-core} calls since the last reset. */
+GNNML3_API int gnnml3_edge_mlp_set_tc(int enable);
+GNNML3_API int gnnml3_edge_mlp_path_counts(long long* out2_host, int reset);
 GNNML3_API int gnnml3_edge_mlp_fwd(const float* ea, const int32_t* eperm, const float* w1, const float* w2, const float* w3,
                         const float* w4, int64_t E, int K, int Kout, float* out, void* stream);
 GNNML3_API size_t gnnml3_edge_mlp_bwd_workspace_bytes(int64_t E, int K);

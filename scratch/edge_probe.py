@@ -14,7 +14,10 @@ def timeit(fn, name, reps=10):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e) * 1e3)
-    ts.sort(); print("%-20s median %8.1f us min %8.1f us" % (name, ts[len(ts) // 2], ts[0]), flush=True)
-timeit(lambda: ops.edge_mlp_fwd(ea, None, w1, w2, w3, w4), "edge_mlp_fwd")
-timeit(lambda: ops.edge_mlp_bwd(ea, None, go, w1, w2, w3, w4, need_dea=False), "edge_mlp_bwd")
-timeit(lambda: ops.edge_mlp_bwd(ea, None, go, w1, w2, w3, w4, need_dea=True), "edge_mlp_bwd+dea")
+    ts.sort(); print("%-30s median %8.1f us min %8.1f us" % (name, ts[len(ts) // 2], ts[0]), flush=True)
+for gen in (True, False):
+    ops.edge_mlp_set_tc(gen)
+    tag = "tcgen05 " if gen else "fp32 fma "
+    timeit(lambda: ops.edge_mlp_fwd(ea, None, w1, w2, w3, w4), tag + "edge_mlp_fwd")
+    timeit(lambda: ops.edge_mlp_bwd(ea, None, go, w1, w2, w3, w4, need_dea=False), tag + "edge_mlp_bwd")
+    timeit(lambda: ops.edge_mlp_bwd(ea, None, go, w1, w2, w3, w4, need_dea=True), tag + "edge_mlp_bwd+dea")

@@ -13,9 +13,21 @@ from oracle import gnnml3_oracle as O  # noqa: E402
 from test_gpu_kernels import assert_close, dev  # noqa: E402
 
 
+@pytest.fixture(params=["tcgen05", "fma"])
+def edge_mlp_generation(request):
+    """Both generations of the edge-MLP kernels serve the same C entry points; run the parity cases through each."""
+    from gnn_matlang_b200 import ops
+    old = ops.edge_mlp_set_tc(request.param == "tcgen05")
+    ops.edge_mlp_path_counts(reset=True)
+    yield request.param
+    tc, fma = ops.edge_mlp_path_counts()
+    ops.edge_mlp_set_tc(old)
+    assert (tc > 0 and fma == 0) if request.param == "tcgen05" else (fma > 0 and tc == 0)
+
+
 @pytest.mark.parametrize("K", [2, 4, 6, 8, 10, 12, 14, 16])
 @pytest.mark.parametrize("E", [1, 255, 1000, 70000])
-def test_edge_mlp_kernels(K, E):
+def test_edge_mlp_kernels(K, E, edge_mlp_generation):
     from gnn_matlang_b200 import ops
     g = torch.Generator().manual_seed(K * 100 + E)
     ea = torch.randn(E, K, generator=g)
@@ -39,6 +51,53 @@ def test_edge_mlp_kernels(K, E):
     for i in range(4):
         assert_close(dws2[i], ws_r[i].grad, rtol=2e-5, name="edge mlp dW%d (sorted)" % (i + 1))
         assert torch.equal(dws2[i], dws3[i])
+
+
+def test_edge_mlp_tensor_core_large_and_generations_agree():
+    """ZINC-step sized call (1.1 M support entries, K = 8): the tcgen05 kernels against the FP32-FMA kernels of round 1 and
+    against float64 (every worker group of every CTA busy, ragged last tile).  Edges with a ReLU input within 1e-4 of zero are
+    dropped from the input: two FP32 evaluations may put such a pre-activation on different sides of the kink, and one flipped
+    mask moves d ea and dW by O(1) -- the discontinuity of the function, not an error of either kernel."""
+    from gnn_matlang_b200 import ops
+    E, K = 1120525, 8
+    g = torch.Generator().manual_seed(11)
+    d = dev()
+    ea = torch.randn(E, K, generator=g).to(d)
+    ws = [(torch.randn(2 * K, K, generator=g) * 0.5).to(d) for _ in range(3)] + [(torch.randn(K, 4 * K, generator=g) * 0.3).to(d)]
+
+    def f64(ea_, ws_):
+        p1 = ea_ @ ws_[0].t()
+        tmp = torch.cat([torch.relu(p1), torch.tanh(ea_ @ ws_[1].t()) * torch.tanh(ea_ @ ws_[2].t())], 1)
+        p4 = tmp @ ws_[3].t()
+        return p1, p4
+
+    p1, p4 = f64(ea.double(), [w.double() for w in ws])
+    keep = (torch.cat([p1, p4], 1).abs().min(1).values > 1e-4)
+    ea = ea[keep].contiguous()
+    E = ea.size(0)
+    assert E > 1100000 and E % 128 != 0
+    gout = torch.randn(E, K, generator=g).to(d)
+    res = {}
+    for gen in (True, False):
+        old = ops.edge_mlp_set_tc(gen)
+        try:
+            out = ops.edge_mlp_fwd(ea, None, *ws)
+            dea, dws = ops.edge_mlp_bwd(ea, None, gout, *ws, need_dea=True)
+            _, dws_b = ops.edge_mlp_bwd(ea, None, gout, *ws, need_dea=False)
+        finally:
+            ops.edge_mlp_set_tc(old)
+        res[gen] = (out, dea, dws, dws_b)
+    assert_close(res[True][0], res[False][0], name="edge mlp fwd, tcgen05 vs fma")
+    assert_close(res[True][1], res[False][1], name="edge mlp d ea, tcgen05 vs fma")
+    ea64 = ea.double().requires_grad_(True)
+    ws64 = [w.double().requires_grad_(True) for w in ws]
+    out64 = torch.relu(f64(ea64, ws64)[1])
+    out64.backward(gout.double())
+    assert_close(res[True][0], out64.float(), name="edge mlp fwd, tcgen05 vs float64")
+    assert_close(res[True][1], ea64.grad.float(), name="edge mlp d ea, tcgen05 vs float64")
+    for i in range(4):
+        assert_close(res[True][2][i], ws64[i].grad.float(), rtol=2e-5, name="edge mlp dW%d, tcgen05 vs float64" % (i + 1))
+        assert_close(res[True][3][i], ws64[i].grad.float(), rtol=2e-5, name="edge mlp dW%d without d ea, tcgen05 vs float64" % (i + 1))
 
 
 @pytest.mark.parametrize("mean", [False, True])
