@@ -71,4 +71,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return copysignf(r, x);
 }
 
+// Same function without the |x| / copysign mirror: e^{2x} = inf gives 1 - 0, e^{2x} = 0 gives 1 - 2; five instructions
+// (FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA).  Same absolute error bound.
+__device__ __forceinline__ float tanh_fast5(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
 }  // namespace gnnml3

@@ -9,9 +9,12 @@
 //     results come back with tcgen05.ld into the same thread.  Nothing edge-dependent crosses threads, so no shared
 //     memory staging, no transposes and no bank conflicts are involved in the forward pass.
 //   * the weights are the B operands: K-major SWIZZLE_128B planes built once per CTA in shared memory, rows = output
-//     features with the TF32 hi parts in the first half and the residuals lo = w - hi in the second half.  One
-//     instruction  D[:, 0:2N] = A_raw [W_hi | W_lo]^T  plus one  D[:, 0:N] += A_lo W_hi^T  per 8-wide k-step give the
-//     error-compensated 3xTF32 product (FP32-grade; the tensor core truncates the raw FP32 operand to its hi part itself).
+//     features with the TF32 hi parts in the first half and the residuals lo = w - hi in the second half.  Three
+//     instructions per 8-wide k-step,  D += A_raw W_hi^T,  D += A_raw W_lo^T,  D += A_lo W_hi^T,  accumulate the
+//     error-compensated 3xTF32 product in ONE set of columns (FP32-grade; the tensor core truncates the raw FP32 operand to
+//     its hi part itself).  The tensor pipe is 15 % busy, instruction issue is what bounds the kernel: summing the
+//     partial products in the accumulator instead of in registers removed a third of the tcgen05.ld traffic and 72 FADDs
+//     per edge.
 //   * edge-feature widths are padded to P = 8 or 16 (k-steps of 8), the three first-layer branches sit at plane rows
 //     0 / 2P / 4P, so that every tensor-memory region is a whole number of 16-column blocks and the activations can be
 //     computed block by block IN PLACE (the block of hidden activations overwrites exactly the pre-activation columns it
@@ -29,28 +32,36 @@
 
 namespace gnnml3 {
 
+#ifndef EMT_MAXWG
+#define EMT_MAXWG 4
+#endif
+
 template <int K>
 struct EMT {
     using C = EMC<K>;
     static constexpr int P = (K + 7) / 8 * 8;           // padded edge-feature width: 8 or 16
     static constexpr int HP = 2 * P, TP = 4 * P, DPP = 6 * P;
-    static constexpr int N1H = 6 * P, N1F = 12 * P;     // first layer: [W1;W2;W3] rows (hi half | hi + lo)
-    static constexpr int N2H = 16, N2F = 32;            // second layer: W4 rows
-    static constexpr int N3H = TP, N3F = 2 * TP;        // d tmp = d pre4 W4: W4^T rows
+    static constexpr int N1 = 6 * P;                    // first layer: [W1;W2;W3] rows (hi rows, then as many lo rows)
+    static constexpr int N2 = 16;                       // second layer and d ea: W4 / W123^T rows
+    static constexpr int N3 = TP;                       // d tmp = d pre4 W4: W4^T rows
     static constexpr int TB = TP / 32;                  // 128-byte column blocks of the second layer's contraction
     static constexpr int DB = (DPP + 31) / 32;          // ... of the d ea contraction over the 6P pre-activation gradients
-    static constexpr int B1_BYTES = N1F * 128, B2_BYTES = TB * 32 * 128, B3_BYTES = N3F * 128, B4_BYTES = DB * 32 * 128;
-    static constexpr int XC = 12 * P, YC = 32, SLOT = XC + YC;   // tensor-memory columns of one worker group
+    static constexpr int B1_BYTES = 2 * N1 * 128, B2_BYTES = TB * 32 * 128, B3_BYTES = 2 * N3 * 128, B4_BYTES = DB * 32 * 128;
+    // tensor-memory columns of one worker group: X = pre123 (6P) -> hidden raw | lo (8P) -> d tmp (4P) -> d pre123 raw | lo (12P);
+    // Y = ea raw | lo (2P) -> pre4 (16) -> d pre4 raw | lo (2P) -> d ea (16)
+    __host__ __device__ static constexpr int xc(int mode) { return mode > 1 ? 12 * P : 8 * P; }
+    static constexpr int YC = 2 * P;
+    __host__ __device__ static constexpr int slot(int mode) { return xc(mode) + YC; }
     __host__ __device__ static constexpr int plane_bytes(int mode) { return B1_BYTES + B2_BYTES + (mode > 0 ? B3_BYTES : 0) + (mode > 1 ? B4_BYTES : 0); }
     static constexpr int stage_bytes = 128 * C::S * 4;
     static constexpr int SMEM_MAX = 227 * 1024 - 1024;  // minus the 1024-byte alignment slack
     __host__ __device__ static constexpr int nwg(int mode) {
-        int n = 512 / SLOT;
+        int n = 512 / slot(mode);
         if (mode > 0) {
             const int m = (SMEM_MAX - plane_bytes(mode) - 64) / stage_bytes;
             n = m < n ? m : n;
         }
-        return n < 1 ? 1 : (n > 4 ? 4 : n);
+        return n < 1 ? 1 : (n > EMT_MAXWG ? EMT_MAXWG : n);
     }
     __host__ __device__ static constexpr int smem_bytes(int mode) { return 1024 + plane_bytes(mode) + 64 + (mode > 0 ? nwg(mode) * stage_bytes : 0); }
     // phase 2 (weight gradients) on 128 threads
@@ -58,6 +69,14 @@ struct EMT {
     static constexpr int TPT = (NT + 127) / 128;        // 4x4 output tiles per thread
     static constexpr int GROUPS = NT >= 128 ? 1 : 128 / NT;
 };
+
+#ifdef EMT_PROFILE
+// measurement build (-DEMT_PROFILE, scratch/edge_phase_probe.py): cycles per phase of worker group 0 / warp 0 of every CTA
+__device__ unsigned long long g_emt_dbg[16];
+#define EMT_T(i) do { if (prof) { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define EMT_T(i) do { } while (0)
+#endif
 
 struct EMTParams {
     const float* ea;
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
     constexpr int P = T::P, HP = T::HP, TP = T::TP, H = C::H;
     constexpr int NWG = T::nwg(MODE);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // (offset arithmetic keeps the shared address space)
     uint8_t* b1 = smem;
     uint8_t* b2 = b1 + T::B1_BYTES;
     uint8_t* b3 = b2 + T::B2_BYTES;
@@ -165,11 +184,11 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
 
     const int wg = threadIdx.x >> 7, t = threadIdx.x & 127, warp_in_wg = t >> 5;
 
-    // ------------------------------------------------------------------ weight planes (hi rows | lo rows), built by all threads
-    for (int i = threadIdx.x; i < T::N1F * P; i += blockDim.x) {
+    // ------------------------------------------------------------------ weight planes (hi rows, then lo rows), built by all threads
+    for (int i = threadIdx.x; i < 2 * T::N1 * P; i += blockDim.x) {
         const int n = i / P, c = i % P;
-        const bool lo = n >= T::N1H;
-        const int nn = lo ? n - T::N1H : n, b = nn / HP, j = nn % HP;
+        const bool lo = n >= T::N1;
+        const int nn = lo ? n - T::N1 : n, b = nn / HP, j = nn % HP;
         const float* w = b == 0 ? p.w1 : (b == 1 ? p.w2 : p.w3);
         emt_put(b1, n, c, (j < H && c < K) ? __ldg(w + j * K + c) : 0.f, lo);
     }
@@ -180,10 +199,10 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
         emt_put(b2 + tb * 4096, n, c, (k < K && j < H) ? __ldg(p.w4 + k * C::T + part * H + j) : 0.f, lo);
     }
     if constexpr (MODE > 0) {
-        for (int i = threadIdx.x; i < T::N3F * P; i += blockDim.x) {
+        for (int i = threadIdx.x; i < 2 * T::N3 * P; i += blockDim.x) {
             const int n = i / P, c = i % P;
-            const bool lo = n >= T::N3H;
-            const int q = lo ? n - T::N3H : n, part = q / HP, j = q % HP;
+            const bool lo = n >= T::N3;
+            const int q = lo ? n - T::N3 : n, part = q / HP, j = q % HP;
             emt_put(b3, n, c, (c < K && j < H) ? __ldg(p.w4 + c * C::T + part * H + j) : 0.f, lo);
         }
     }
@@ -208,19 +227,24 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
     const uint32_t tmem_base = *tmem_slot;
 
     // ------------------------------------------------------------------ per-group state
-    const uint32_t Xm = tmem_base + (uint32_t)wg * T::SLOT, Ym = Xm + T::XC;       // MMA operand addresses (lane 0)
+    const uint32_t Xm = tmem_base + (uint32_t)wg * T::slot(MODE), Ym = Xm + T::xc(MODE);     // MMA operand addresses (lane 0)
     const uint32_t lane_sel = (uint32_t)(warp_in_wg * 32) << 16;
-    const uint32_t X = Xm + lane_sel, Y = Ym + lane_sel;                            // this warp's lane quarter
+    const uint32_t X = Xm + lane_sel, Y = Ym + lane_sel;                                      // this warp's lane quarter
     uint64_t* bar = bars + wg;
     uint32_t ph = 0;
     const int barid = 1 + wg;
-    const uint64_t d1 = make_kmajor_sw128_desc(smem_u32(b1));
-    const uint64_t d2 = make_kmajor_sw128_desc(smem_u32(b2));
-    const uint64_t d3 = make_kmajor_sw128_desc(smem_u32(b3));
-    const uint64_t d4 = make_kmajor_sw128_desc(smem_u32(b4));
-    constexpr uint32_t ID1F = make_idesc_tf32_mn(128, T::N1F), ID1H = make_idesc_tf32_mn(128, T::N1H);
-    constexpr uint32_t ID2F = make_idesc_tf32_mn(128, T::N2F), ID2H = make_idesc_tf32_mn(128, T::N2H);
-    constexpr uint32_t ID3F = make_idesc_tf32_mn(128, T::N3F), ID3H = make_idesc_tf32_mn(128, T::N3H);
+    // B descriptors: hi rows first, lo rows behind them (whole 8-row groups: every offset is a multiple of 1024 bytes)
+    const uint64_t d1h = make_kmajor_sw128_desc(smem_u32(b1)), d1l = d1h + (uint64_t)((T::N1 * 128) >> 4);
+    const uint64_t d2h = make_kmajor_sw128_desc(smem_u32(b2)), d2l = d2h + (uint64_t)((16 * 128) >> 4);
+    const uint64_t d3h = make_kmajor_sw128_desc(smem_u32(b3)), d3l = d3h + (uint64_t)((T::N3 * 128) >> 4);
+    const uint64_t d4h = make_kmajor_sw128_desc(smem_u32(b4)), d4l = d4h + (uint64_t)((16 * 128) >> 4);
+    constexpr uint32_t ID1 = make_idesc_tf32_mn(128, T::N1), ID2 = make_idesc_tf32_mn(128, T::N2), ID3 = make_idesc_tf32_mn(128, T::N3);
+    // the three products of one k-step: raw x hi, raw x lo, lo x hi
+    auto mma3 = [&](uint32_t d, uint32_t a_raw, uint32_t a_lo, uint64_t bh, uint64_t bl, uint32_t idesc, bool first) {
+        emt_mma(d, a_raw, bh, idesc, first ? 0u : 1u);
+        emt_mma(d, a_raw, bl, idesc, 1u);
+        emt_mma(d, a_lo, bh, idesc, 1u);
+    };
 
     float* stage = stage_all + (size_t)wg * 128 * C::S;
     float* row = stage + (size_t)t * C::S;
@@ -252,9 +276,8 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
 
     const int64_t ntiles = (p.E + 127) / 128;
     const int64_t tstride = (int64_t)gridDim.x * NWG;
-    // this thread's rows of ea (and of the upstream gradient) are fetched one tile ahead: the loads of tile i + 1 fly during
-    // the tensor-core round trips of tile i (ncu: 26 % of the forward's stall samples sat on this load before)
-    // (the upstream gradient row is loaded at the top of its own tile and first used two round trips later)
+    // this thread's row of ea is fetched one tile ahead (the upstream gradient row is loaded at the top of its own tile and
+    // first used two round trips later)
     float in_n[C::KP];
     int64_t src_n = 0;
     auto fetch = [&](int64_t tile) {
@@ -268,6 +291,11 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
         }
     };
     fetch((int64_t)blockIdx.x * NWG + wg);
+#ifdef EMT_PROFILE
+    const bool prof = t == 0;
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    const long long tbegin = tlast;
+#endif
     for (int64_t tile = (int64_t)blockIdx.x * NWG + wg; tile < ntiles; tile += tstride) {
         const int64_t e = tile * 128 + t;
         const bool live = e < p.E;
@@ -275,14 +303,7 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
         float in[P];
 #pragma unroll
         for (int i = 0; i < P; ++i) in[i] = i < C::KP ? in_n[i < C::KP ? i : 0] : 0.f;
-        float go[C::KP];
-#pragma unroll
-        for (int i = 0; i < C::KP; ++i) go[i] = 0.f;
-        if constexpr (MODE > 0) {
-            if (live) load_edge_row<K>(p.gout + e * K, go);
-        }
-        fetch(tile + tstride);
-        // ---------------------------------------------------------------- layer 1: pre123 = ea [W1;W2;W3]^T
+        // ---------------------------------------------------------------- layer 1: pre123 = ea [W1;W2;W3]^T -> X [0, 6P)
         {
             float lo[P];
 #pragma unroll
@@ -299,44 +320,41 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
 #pragma unroll
             for (int i = 0; i < C::KP; i += 4) *reinterpret_cast<float4*>(row + C::OFF_IN + i) = make_float4(in[i], in[i + 1], in[i + 2], in[i + 3]);
         }
+        // Global loads are issued only now, AFTER the last use of the previous fetch: the hardware scoreboard counts per slot,
+        // not per register, so a consumer of the old row that waits on its slot would also wait for loads issued before it
+        // (ncu: 25 % of the forward's stall samples sat on the first emt_lo with the fetch placed at the top of the tile).
+        float go[C::KP];
+#pragma unroll
+        for (int i = 0; i < C::KP; ++i) go[i] = 0.f;
+        if constexpr (MODE > 0) {
+            if (live) load_edge_row<K>(p.gout + e * K, go);
+        }
+        fetch(tile + tstride);
+        EMT_T(0);      // loads + first stores
         emt_round(barid, warp_in_wg, bar, ph, [&] {
 #pragma unroll
-            for (int s = 0; s < P / 8; ++s) {
-                emt_mma(Xm, Ym + 8 * s, d1 + (uint64_t)(2 * s), ID1F, s > 0 ? 1u : 0u);
-                emt_mma(Xm, Ym + P + 8 * s, d1 + (uint64_t)(2 * s), ID1H, 1u);
-            }
+            for (int s = 0; s < P / 8; ++s) mma3(Xm, Ym + 8 * s, Ym + P + 8 * s, d1h + (uint64_t)(2 * s), d1l + (uint64_t)(2 * s), ID1, s == 0);
         });
+        EMT_T(1);      // round trip 1
         // ---------------------------------------------------------------- activations, 16 hidden units at a time, in place:
-        // reads   pre1 [c16, +16) | pre2 [2P + c16) | pre3 [4P + c16) and the lo-weight partial sums 6P further
+        // reads   pre1 [c16, +16) | pre2 [2P + c16) | pre3 [4P + c16)
         // writes  relu raw [c16) | product raw [2P + c16) | relu lo [4P + c16) | product lo [6P + c16)   (= A operand of layer 2:
         //         raw tmp in columns [0, 4P), residuals in [4P, 8P))
         uint32_t mask1 = 0;
 #pragma unroll
         for (int c = 0; c < HP / 16; ++c) {
-            float a1[16], a2[16], a3[16];
-            {
-                float l1[16], l2[16], l3[16];
-                emt_ld16(X + 16 * c, a1);
-                emt_ld16(X + 6 * P + 16 * c, l1);
-                emt_ld16(X + 2 * P + 16 * c, a2);
-                emt_ld16(X + 8 * P + 16 * c, l2);
-                emt_ld16(X + 4 * P + 16 * c, a3);
-                emt_ld16(X + 10 * P + 16 * c, l3);
-                emt_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    a1[i] += l1[i];
-                    a2[i] += l2[i];
-                    a3[i] += l3[i];
-                }
-            }
-            float r[16], pr[16];
+            float r[16], a2[16], a3[16];
+            emt_ld16(X + 16 * c, r);
+            emt_ld16(X + 2 * P + 16 * c, a2);
+            emt_ld16(X + 4 * P + 16 * c, a3);
+            emt_ld_wait();
+            float pr[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                r[i] = fmaxf(a1[i], 0.f);
-                if (a1[i] > 0.f) mask1 |= 1u << (16 * c + i);
-                a2[i] = tanh_fast(a2[i]);
-                a3[i] = tanh_fast(a3[i]);
+                if (MODE > 0 && r[i] > 0.f) mask1 |= 1u << (16 * c + i);
+                r[i] = fmaxf(r[i], 0.f);
+                a2[i] = tanh_fast5(a2[i]);
+                a3[i] = tanh_fast5(a3[i]);
                 pr[i] = a2[i] * a3[i];
             }
             emt_st16(X + 16 * c, r);
@@ -362,24 +380,19 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
             emt_st16(X + 4 * P + 16 * c, r);
             emt_st16(X + 6 * P + 16 * c, pr);
         }
-        // ---------------------------------------------------------------- layer 2: pre4 = tmp W4^T -> Y [0, 16) hi weights, [16, 32) lo
+        EMT_T(2);      // activations
+        // ---------------------------------------------------------------- layer 2: pre4 = tmp W4^T -> Y [0, 16)
         emt_round(barid, warp_in_wg, bar, ph, [&] {
 #pragma unroll
             for (int s = 0; s < TP / 8; ++s) {
-                const uint64_t d = d2 + (uint64_t)((s / 4) * (4096 >> 4) + 2 * (s % 4));
-                emt_mma(Ym, Xm + 8 * s, d, ID2F, s > 0 ? 1u : 0u);
-                emt_mma(Ym, Xm + TP + 8 * s, d, ID2H, 1u);
+                const uint64_t adv = (uint64_t)((s / 4) * (4096 >> 4) + 2 * (s % 4));
+                mma3(Ym, Xm + 8 * s, Xm + TP + 8 * s, d2h + adv, d2l + adv, ID2, s == 0);
             }
         });
+        EMT_T(3);      // round trip 2
         float pre4[16];
-        {
-            float l4[16];
-            emt_ld16(Y, pre4);
-            emt_ld16(Y + 16, l4);
-            emt_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pre4[i] += l4[i];
-        }
+        emt_ld16(Y, pre4);
+        emt_ld_wait();
         if constexpr (MODE == 0) {
             if (live) {
                 float* op = p.out + e * K;
@@ -387,7 +400,7 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
                 for (int k = 0; k < K; k += 2) *reinterpret_cast<float2*>(op + k) = make_float2(fmaxf(pre4[k], 0.f), fmaxf(pre4[k + 1], 0.f));
             }
         } else {
-            // ------------------------------------------------------------ d pre4 = gout * relu'(pre4);  d tmp = d pre4 W4
+            // ------------------------------------------------------------ d pre4 = gout * relu'(pre4);  d tmp = d pre4 W4 -> X [0, 4P)
             float dp4[P];
 #pragma unroll
             for (int k = 0; k < P; ++k) dp4[k] = (k < K && pre4[k] > 0.f) ? go[k < C::KP ? k : 0] : 0.f;
@@ -407,29 +420,17 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
             }
             emt_round(barid, warp_in_wg, bar, ph, [&] {
 #pragma unroll
-                for (int s = 0; s < P / 8; ++s) {
-                    emt_mma(Xm, Ym + 8 * s, d3 + (uint64_t)(2 * s), ID3F, s > 0 ? 1u : 0u);
-                    emt_mma(Xm, Ym + P + 8 * s, d3 + (uint64_t)(2 * s), ID3H, 1u);
-                }
+                for (int s = 0; s < P / 8; ++s) mma3(Xm, Ym + 8 * s, Ym + P + 8 * s, d3h + (uint64_t)(2 * s), d3l + (uint64_t)(2 * s), ID3, s == 0);
             });
-            // d tmp: relu part in X [c16) (+ lo-weight sums at 4P), product part in X [2P + c16) (+ 6P).  In place (mode 2):
+            EMT_T(4);  // d pre4 + round trip 3
+            // d tmp: relu part in X [c16), product part in X [2P + c16).  In place (mode 2):
             // d pre1 raw [c16) | d pre2 raw [2P + c16) | d pre3 raw [4P + c16) | residuals 6P further
 #pragma unroll
             for (int c = 0; c < HP / 16; ++c) {
                 float dt1[16], dt2[16];
-                {
-                    float l1[16], l2[16];
-                    emt_ld16(X + 16 * c, dt1);
-                    emt_ld16(X + 4 * P + 16 * c, l1);
-                    emt_ld16(X + 2 * P + 16 * c, dt2);
-                    emt_ld16(X + 6 * P + 16 * c, l2);
-                    emt_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        dt1[i] += l1[i];
-                        dt2[i] += l2[i];
-                    }
-                }
+                emt_ld16(X + 16 * c, dt1);
+                emt_ld16(X + 2 * P + 16 * c, dt2);
+                emt_ld_wait();
                 float g1[16], g2[16], g3[16];
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
@@ -472,35 +473,38 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
                 for (int i = C::D; i < C::DP; ++i) row[C::OFF_D + i] = 0.f;
             }
             if constexpr (MODE > 1) {
-                // -------------------------------------------------------- d ea = d pre123 [W1;W2;W3] -> Y [0, 16) hi weights, [16, 32) lo
+                // -------------------------------------------------------- d ea = d pre123 [W1;W2;W3] -> Y [0, 16)
                 emt_round(barid, warp_in_wg, bar, ph, [&] {
 #pragma unroll
                     for (int s = 0; s < T::DPP / 8; ++s) {
-                        const uint64_t d = d4 + (uint64_t)((s / 4) * (4096 >> 4) + 2 * (s % 4));
-                        emt_mma(Ym, Xm + 8 * s, d, ID2F, s > 0 ? 1u : 0u);
-                        emt_mma(Ym, Xm + T::DPP + 8 * s, d, ID2H, 1u);
+                        const uint64_t adv = (uint64_t)((s / 4) * (4096 >> 4) + 2 * (s % 4));
+                        mma3(Ym, Xm + 8 * s, Xm + T::DPP + 8 * s, d4h + adv, d4l + adv, ID2, s == 0);
                     }
                 });
-                float din[16], l[16];
+                float din[16];
                 emt_ld16(Y, din);
-                emt_ld16(Y + 16, l);
                 emt_ld_wait();
                 if (live) {
                     float* dp = p.dea + src * K;
 #pragma unroll
-                    for (int i = 0; i < K; i += 2) *reinterpret_cast<float2*>(dp + i) = make_float2(din[i] + l[i], din[i + 1] + l[i + 1]);
+                    for (int i = 0; i < K; i += 2) *reinterpret_cast<float2*>(dp + i) = make_float2(din[i], din[i + 1]);
                 }
-                tc_fence_before();      // the next tile's tcgen05.st reuses Y
             }
+            EMT_T(5);  // pre-activation gradients (+ d ea round trip)
             // ------------------------------------------------------------ phase 2: outer products over the group's 128 staged edges
             emt_group_sync(barid);
+            EMT_T(6);  // group barrier before phase 2
 #pragma unroll
             for (int u = 0; u < T::TPT; ++u) {
                 if (accum[u]) {
+                    const float* pa = stage + (size_t)group * C::S + offA[u];
+                    const float* pb = stage + (size_t)group * C::S + offB[u];
 #pragma unroll 4
                     for (int r = group; r < 128; r += T::GROUPS) {
-                        const float4 a = *reinterpret_cast<const float4*>(stage + (size_t)r * C::S + offA[u]);
-                        const float4 b = *reinterpret_cast<const float4*>(stage + (size_t)r * C::S + offB[u]);
+                        const float4 a = *reinterpret_cast<const float4*>(pa);
+                        const float4 b = *reinterpret_cast<const float4*>(pb);
+                        pa += T::GROUPS * C::S;
+                        pb += T::GROUPS * C::S;
                         const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
@@ -510,8 +514,17 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
                 }
             }
             emt_group_sync(barid);
+            EMT_T(7);  // phase 2
         }
+        EMT_T(8);      // output store
     }
+#ifdef EMT_PROFILE
+    if (prof && wg == 0) {
+        for (int i = 0; i < 9; ++i) atomicAdd(&g_emt_dbg[i], (unsigned long long)tacc[i]);
+        atomicAdd(&g_emt_dbg[9], (unsigned long long)(clock64() - tbegin));
+        atomicAdd(&g_emt_dbg[10], 1ull);
+    }
+#endif
     if constexpr (MODE > 0) {
         // reduce the thread groups of this worker group in a fixed order and emit its partial (tile layout of k_edge_mlp_bwd)
         float* red = stage;   // [GROUPS][NT * 16]
@@ -603,3 +616,15 @@ int edge_mlp_tc_bwd(const float* ea, const int32_t* eperm, const float* gout, co
 }
 
 }  // namespace gnnml3
+
+#ifdef EMT_PROFILE
+extern "C" __attribute__((visibility("default"))) int gnnml3_emt_debug_fetch(unsigned long long* host16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host16, gnnml3::g_emt_dbg, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {};
+        cudaMemcpyToSymbol(gnnml3::g_emt_dbg, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
