@@ -64,12 +64,12 @@ SIGNATURES = {
     "gnnml3_fused_path_counts": (_i, [_p, _i]),
     "gnnml3_fused_sddmm_supported": (_i, [_i, _i, _i]),
     "gnnml3_fused_sddmm_workspace_bytes": (_sz, [_i]),
-    "gnnml3_fused_sddmm": (_i, [_p, _p, _p, _i64, _i, _p, _i64, _i, _p, _i, _i64, _p, _p, _sz, _p]),
+    "gnnml3_fused_sddmm": (_i, [_p, _p, _p, _p, _i64, _i, _p, _i64, _i, _p, _i, _i64, _p, _p, _sz, _p]),
     "gnnml3_ml3layer_supported": (_i, [_i, _i, _i, _i, _i]),
     "gnnml3_ml3layer_workspace_bytes": (_sz, [_i64, _i64, _i, _i, _i, _i]),
     "gnnml3_ml3layer_forward": (_i, [_p, _p, _p, _i64, _i64, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p,
                                      _i64, _p, _p, _sz, _p]),
-    "gnnml3_ml3layer_backward": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i,
+    "gnnml3_ml3layer_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i,
                                       _p, _i64, _p, _p, _i64, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gnnml3_segment_pool_fwd": (_i, [_p, _i64, _p, _i, _i, _i, _p, _p]),
     "gnnml3_segment_pool_bwd": (_i, [_p, _p, _i, _i, _i, _p, _i64, _p]),

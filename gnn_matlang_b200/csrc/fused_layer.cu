@@ -159,7 +159,7 @@ k_fused_agg_proj(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     constexpr int STAGE_BYTES = HP_BYTES + (RES ? 0 : WPLANE);
     static_assert(NMMA <= 256 && NMMA % 16 == 0, "bad tile size");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const int nkb_total = P.nkb_main + (P.self_mode != 0 ? 1 : 0);
     const int nstages = P.nstages;
     uint8_t* wres = smem;                                                               // [nkb_total][WPLANE] if RES

@@ -332,7 +332,7 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUt
     constexpr int WPLANE = 2 * BNH * 128;               // bytes of one weight plane: rows [W_hi^T ; W_lo^T] x 32 k-columns
     constexpr uint32_t ID_FULL = make_idesc_tf32_mn(128, 2 * BNH), ID_HALF = make_idesc_tf32_mn(128, BNH);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const int nkb_total = P.nkb_main + (P.self_mode != 0 ? 1 : 0);
     const int cap = P.edge_cap;
     const int Kstride = P.Kstride;
@@ -1010,7 +1010,7 @@ static int ts_launch(const CUtensorMap& mW, const CUtensorMap& mX, TSParams& P, 
 
 // X [N, F] (row stride ldx) -> 2-D tensor map with a [box_rows x 32 columns] box, 128B swizzle; columns >= F and rows >= N
 // are zero-filled by the TMA unit
-static int ts_make_xmap(CUtensorMap* map, const float* base, int64_t rows, int F, int64_t ld, int box_rows) {
+int ts_make_xmap(CUtensorMap* map, const float* base, int64_t rows, int F, int64_t ld, int box_rows) {
     PFN_encodeTiled enc = get_encoder();
     if (!enc) return set_err(GNNML3_ERR_CUDA, "fused_agg_proj: cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)rows};

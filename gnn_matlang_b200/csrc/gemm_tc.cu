@@ -67,7 +67,7 @@ k_gemm_nn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     using Cfg = TCCfg<BN>;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * Cfg::STAGE_BYTES);
     uint64_t* raw_full = bars;                         // [STAGES]  TMA bytes landed              -> splitters
     uint64_t* full = bars + TC_STAGES;                 // [STAGES]  lo plane written              -> MMA

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1)
 k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ P,
              int64_t M, int Ka, int Nb, int64_t rows_per_cta) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     __shared__ uint64_t raw[TT_HI], full[TT_HI], mdone[TT_HI], done;
     __shared__ uint32_t tslot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
@@ -146,6 +146,10 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     if (nst > 0) {
         mbar_wait(&done, 0);
         tc_fence_after();
+        // every MMA that read the stage ring has retired (commit -> `done`) and every split warp finished its reads before its last
+        // arrival, so `outs` may reuse the ring; the CTA barrier states that ordering in a form compute-sanitizer's racecheck can see
+        // (it does not follow mbarrier / tcgen05.commit edges and reported the reuse as a hazard)
+        __syncthreads();
         if (warp < 4) {
             // lanes 0-15 of warp w: D1 rows 16w..16w+15; lanes 16-31: D2 rows 16w..16w+15 (accumulator at lane offset 16)
             const int mrow = 16 * warp + (lane & 15);

@@ -154,8 +154,8 @@ extern "C" int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col
                                  Fo, wg, 2 * G, 2 * G, bconv, bg, N, Fo, y, ldy, aux, 2 * G, G, 1, nullptr, 0, win, ws + w.fused, w.wg - w.fused, stream);
 }
 
-extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* rowptrT, const int32_t* colT,
-                                        const int32_t* permT, const int32_t* winT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
+extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* win, const int32_t* rowptrT,
+                                        const int32_t* colT, const int32_t* permT, const int32_t* winT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
                                         const float* ea_s, const float* ea2, int K, const float* w1, const float* w2, const float* w3,
                                         const float* w4, const float* wconv, int Fo, const float* w11, const float* w12, int G,
                                         const float* y, int64_t ldy, const float* aux, const float* gy, int64_t ldgy, int need_dx,
@@ -223,7 +223,7 @@ extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* co
     // edge-feature gradient: fused dH + SDDMM, then back through the edge MLP
     if (w1 || need_dea) {
         float* dea2 = w1 ? (float*)(ws + w.dea2) : dea;
-        if ((rc = gnnml3_fused_sddmm(rowptr, col, x, ldx, Fi, gpre, w.ldg, Fo, wconv, K, N, dea2, ws + w.sd, w.emlp - w.sd, stream))) return rc;
+        if ((rc = gnnml3_fused_sddmm(rowptr, col, win, x, ldx, Fi, gpre, w.ldg, Fo, wconv, K, N, dea2, ws + w.sd, w.emlp - w.sd, stream))) return rc;
         if (w1) {
             if ((rc = gnnml3_edge_mlp_bwd(ea_s, nullptr, dea2, w1, w2, w3, w4, E, K, K, need_dea ? dea : nullptr, dw1, dw2, dw3, dw4,
                                           ws + w.emlp, w.total_bwd - w.emlp, stream)))

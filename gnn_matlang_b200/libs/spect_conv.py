@@ -148,7 +148,7 @@ class _SpectConvFn(torch.autograd.Function):
             if plan.E == 0:
                 dea = torch.zeros_like(ea_s)
             elif ctx.fused and ops.fused_sddmm_supported(K, Fi, Fo):      # (FP32-grade in every mode)
-                dea = ops.fused_sddmm(plan.rowptr, plan.col, x, gout, weight[:K].contiguous(), plan.E)
+                dea = ops.fused_sddmm(plan.rowptr, plan.col, x, gout, weight[:K].contiguous(), plan.E, win=plan.win)
             else:
                 wp = weight[:K].permute(2, 0, 1).reshape(Fo, K * Fi).contiguous()
                 dH = ops.gemm_nn(gout, wp, precision=prec)                   # [N, K*Fi]
@@ -417,7 +417,7 @@ class _ML3LayerFn(torch.autograd.Function):
                 dea2 = torch.zeros_like(ea2)
             elif ctx.fused and ops.fused_sddmm_supported(K, Fi, Fo):
                 # dH = gc [W_0^T ..] tile by tile in tensor memory / shared memory, consumed in place by the SDDMM
-                dea2 = ops.fused_sddmm(plan.rowptr, plan.col, x, gc, wconv, plan.E)
+                dea2 = ops.fused_sddmm(plan.rowptr, plan.col, x, gc, wconv, plan.E, win=plan.win)
             else:
                 wp = wconv.permute(2, 0, 1).reshape(Fo, K * Fi).contiguous()
                 dH = ops.gemm_nn(gc, wp, precision=prec)
@@ -617,6 +617,9 @@ class ML3Layer(torch.nn.Module):
         ea = sorted_edge_attr(edge_attr, plan)
         prec = _PRECISIONS[self.precision]
         c = self.conv1
+        if not self.learnedge and ea.size(1) > c.weight.size(0):
+            # the reference's SpectConv reads edge_attr[:, i] for i < K only (libs/spect_conv.py:76-80): extra channels are ignored
+            ea = ea[:, :c.weight.size(0)].contiguous()
         if ea.size(1) != (self.fc1_1.in_features if self.learnedge else c.weight.size(0)):
             raise RuntimeError("ML3Layer: edge_attr has %d channels, expected %d"
                                % (ea.size(1), self.fc1_1.in_features if self.learnedge else c.weight.size(0)))

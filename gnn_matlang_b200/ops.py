@@ -33,8 +33,11 @@ def _on(device):
 
 
 def _ws(device, nbytes, tag="main"):
-    """Grow-only per-device scratch buffer (stream-ordered reuse on the current stream)."""
-    key = (device.index, tag)
+    """Grow-only scratch buffer per (device, current stream of that device, tag).  Reuse is ordered by the stream the buffer
+    is keyed on: two streams driving the library on one device (evaluation overlapped with training, a side-stream prefetch
+    that runs a layer) get separate buffers instead of overwriting each other's weight planes / partial sums."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch._C._cuda_getCurrentRawStream(idx), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -459,9 +462,10 @@ def fused_sddmm_supported(K, Fi, Fo):
     return bool(_lib.load().gnnml3_fused_sddmm_supported(int(K), int(Fi), int(Fo)))
 
 
-def fused_sddmm(rowptr, col, x, gc, W, E):
+def fused_sddmm(rowptr, col, x, gc, W, E, win=None):
     """dea[p, k] = <x[col[p]], gc[t] W[k]^T> for every CSR slot p of row t (gnnml3_fused_sddmm) -> [E, K].
-    x [N, Fi] and gc [N, Fo] must satisfy ``aligned_rows``; W [K, Fi, Fo]."""
+    x [N, Fi] and gc [N, Fo] must satisfy ``aligned_rows``; W [K, Fi, Fo]; ``win`` = the plan's per-tile source windows of
+    (rowptr, col) (``plan.win``): with them the source rows are staged in shared memory."""
     lib = _lib.load()
     W = _f32c(W, "W")
     K, Fi, Fo = W.shape
@@ -469,7 +473,7 @@ def fused_sddmm(rowptr, col, x, gc, W, E):
     dea = torch.empty(E, K, dtype=torch.float32, device=x.device)
     ws = _ws(x.device, lib.gnnml3_fused_sddmm_workspace_bytes(K), tag="fused_sddmm")
     with _on(x.device):
-        _lib.check(lib.gnnml3_fused_sddmm(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(x), _ld(x), Fi, _lib.ptr(gc), _ld(gc), Fo,
+        _lib.check(lib.gnnml3_fused_sddmm(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(win), _lib.ptr(x), _ld(x), Fi, _lib.ptr(gc), _ld(gc), Fo,
                                           _lib.ptr(W), K, N, _lib.ptr(dea), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                    "gnnml3_fused_sddmm")
     return dea
@@ -530,7 +534,7 @@ def ml3layer_backward(plan, x, ea_s, ea2, ws4, wconv, gates_w, y, aux, gy, need_
     gw = gates_w if gates_w is not None else (None, None)
     with _on(dev):
         _lib.check(lib.gnnml3_ml3layer_backward(
-            p(plan.rowptr), p(plan.col), p(plan.rowptrT), p(plan.colT), p(plan.permT), p(plan.winT), N, E, p(x), _ld(x), Fi, p(ea_s), p(ea2), K,
+            p(plan.rowptr), p(plan.col), p(plan.win), p(plan.rowptrT), p(plan.colT), p(plan.permT), p(plan.winT), N, E, p(x), _ld(x), Fi, p(ea_s), p(ea2), K,
             p(w[0]), p(w[1]), p(w[2]), p(w[3]), p(wconv), Fo, p(gw[0]), p(gw[1]), G, p(y), _ld(y), p(aux), p(gy), _ld(gy),
             int(need_dx), int(need_dea), p(dx), lddx, p(dea), p(dws[0]), p(dws[1]), p(dws[2]), p(dws[3]), p(dwc), p(dbias), p(dw11),
             p(dw12), p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_backward")

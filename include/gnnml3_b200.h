@@ -210,8 +210,10 @@ GNNML3_API int gnnml3_fused_path_counts(long long* out2_host, int reset);
  * --------------------------------------------------------------------------------------------------- */
 GNNML3_API int gnnml3_fused_sddmm_supported(int K, int Fi, int Fo);
 GNNML3_API size_t gnnml3_fused_sddmm_workspace_bytes(int K);
-GNNML3_API int gnnml3_fused_sddmm(const int32_t* rowptr, const int32_t* col, const float* X, int64_t ldx, int Fi, const float* GC,
-                       int64_t ldg, int Fo, const float* W, int K, int64_t N, float* dea, void* workspace,
+/* win (nullable): per-128-row-tile source windows of (rowptr, col) from gnnml3_tile_windows -- with them the source rows of a
+ * tile are staged in shared memory by one TMA box load (batched disjoint graphs); without, every edge gathers from global memory. */
+GNNML3_API int gnnml3_fused_sddmm(const int32_t* rowptr, const int32_t* col, const int32_t* win, const float* X, int64_t ldx, int Fi,
+                       const float* GC, int64_t ldg, int Fo, const float* W, int K, int64_t N, float* dea, void* workspace,
                        size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
@@ -234,8 +236,8 @@ GNNML3_API int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col
                             const float* w4, const float* wconv, const float* bconv, int Fo, const float* w11,
                             const float* b11, const float* w12, const float* b12, int G, float* ea2, float* y,
                             int64_t ldy, float* aux, void* workspace, size_t workspace_bytes, void* stream);
-GNNML3_API int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* rowptrT, const int32_t* colT,
-                             const int32_t* permT, const int32_t* winT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
+GNNML3_API int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* win, const int32_t* rowptrT,
+                             const int32_t* colT, const int32_t* permT, const int32_t* winT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
                              const float* ea_s, const float* ea2, int K, const float* w1, const float* w2, const float* w3,
                              const float* w4, const float* wconv, int Fo, const float* w11, const float* w12, int G,
                              const float* y, int64_t ldy, const float* aux, const float* gy, int64_t ldgy, int need_dx,

@@ -221,10 +221,12 @@ def test_fused_ts_mixed_windows_and_side_output():
     assert_close(hout, H.view(N, K * 32), name="aggregate side output")
 
 
+@pytest.mark.parametrize("staged", [True, False])
 @pytest.mark.parametrize("N,deg,K,Fi,Fo", [(3000, 6, 8, 32, 30), (3001, 5, 8, 25, 30), (1000, 7, 6, 2, 32), (60, 3, 2, 8, 8),
                                            (100000, 6, 8, 32, 30), (2000, 4, 4, 17, 9)])
-def test_fused_sddmm(N, deg, K, Fi, Fo):
-    """d ea[p, k] = <x[col[p]], gc[t] W_k^T> against float64."""
+def test_fused_sddmm(N, deg, K, Fi, Fo, staged):
+    """d ea[p, k] = <x[col[p]], gc[t] W_k^T> against float64; with the plan's source windows (source rows staged in shared
+    memory by TMA) and without (every edge gathers from global memory)."""
     from gnn_matlang_b200 import ops
     ei, g = _graph(N, deg, 3 * N + K, blk=25)
     d = dev()
@@ -232,13 +234,50 @@ def test_fused_sddmm(N, deg, K, Fi, Fo):
     x = torch.randn(N, Fi, generator=g)
     gc = torch.randn(N, Fo, generator=g)
     W = torch.randn(K, Fi, Fo, generator=g) / np.sqrt(Fo)
-    dea = ops.fused_sddmm(plan["rowptr"], plan["col"], ops.aligned_rows(x.to(d)), ops.aligned_rows(gc.to(d)), W.to(d), ei.size(1))
+    dea = ops.fused_sddmm(plan["rowptr"], plan["col"], ops.aligned_rows(x.to(d)), ops.aligned_rows(gc.to(d)), W.to(d), ei.size(1),
+                          win=plan["win"] if staged else None)
     rowptr = plan["rowptr"].cpu().long()
     col = plan["col"].cpu().long()
     dst = torch.repeat_interleave(torch.arange(N), rowptr[1:] - rowptr[:-1])
     dH = torch.einsum("no,kio->nki", gc.double(), W.double())              # [N, K, Fi]
     ref = torch.einsum("ei,eki->ek", x.double()[col], dH[dst])
     assert_close(dea, ref, name="fused sddmm")
+
+
+def test_fused_sddmm_mixed_windows_and_crowded_tiles():
+    """One launch with all three kinds of tiles: local edges (staged), long-range edges (window wider than the TMA box: global
+    gathers) and rows with more CSR slots than the staging buffer holds (global gathers); staged and unstaged results must be
+    bit-identical (same arithmetic, same order)."""
+    from gnn_matlang_b200 import ops
+    N, deg, K, Fi, Fo = 6000, 5, 8, 30, 32
+    g = torch.Generator().manual_seed(17)
+    E = N * deg
+    src = torch.randint(0, N, (E,), generator=g)
+    near = ((src // 40) * 40 + torch.randint(0, 40, (E,), generator=g)).clamp(max=N - 1)
+    far = torch.randint(N // 2, N, (E,), generator=g)
+    dst = torch.where(src < N // 2, near, far)
+    # rows 0..63 receive 40 extra local edges each: 2560 + slots in one 64-row tile (> 1024)
+    xs = torch.randint(0, 64, (64 * 40,), generator=g)
+    xd = torch.arange(64).repeat_interleave(40)
+    ei = torch.stack([torch.cat([src, xs]), torch.cat([dst, xd])])
+    d = dev()
+    plan = ops.csr_build(ei.to(d), N)
+    win = plan["win"].cpu().numpy()
+    width = win[:, 1] - win[:, 0]
+    assert (width <= 256).any() and (width > 256).any()
+    rowptr = plan["rowptr"].cpu().long()
+    assert int(rowptr[64] - rowptr[0]) > 1024
+    x = torch.randn(N, Fi, generator=g)
+    gc = torch.randn(N, Fo, generator=g)
+    W = torch.randn(K, Fi, Fo, generator=g) / np.sqrt(Fo)
+    args = (plan["rowptr"], plan["col"], ops.aligned_rows(x.to(d)), ops.aligned_rows(gc.to(d)), W.to(d), ei.size(1))
+    a = ops.fused_sddmm(*args, win=plan["win"])
+    b = ops.fused_sddmm(*args, win=None)
+    assert torch.equal(a, b)
+    col = plan["col"].cpu().long()
+    dstv = torch.repeat_interleave(torch.arange(N), rowptr[1:] - rowptr[:-1])
+    dH = torch.einsum("no,kio->nki", gc.double(), W.double())
+    assert_close(a, torch.einsum("ei,eki->ek", x.double()[col], dH[dstv]), name="fused sddmm (mixed tiles)")
 
 
 def test_act_bwd_y_layout_and_sums():

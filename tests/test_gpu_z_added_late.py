@@ -69,3 +69,46 @@ def test_isomorphism_known_answers_on_the_gpu():
             eexp = _embed_all(model, graphs_exp)
             assert int(((eexp[0::2] - eexp[1::2]).abs().sum(1) <= 0.001).sum()) == 0
     assert similar8 == [1, 0]
+
+
+def test_two_streams_do_not_share_scratch():
+    """scratch buffers are keyed by (device, stream, tag) -- two streams driving the library at once must
+    not overwrite each other's partial sums.  Edge-MLP backward (per-group partials in the workspace) with different weights on
+    two streams, enqueued back to back, against the same calls made one after the other."""
+    from gnn_matlang_b200 import ops
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    E, K = 300000, 8
+    ea = torch.randn(E, K, generator=g).to(d)
+    go = torch.randn(E, K, generator=g).to(d)
+    wsets = [[(torch.randn(2 * K, K, generator=g) * 0.5).to(d) for _ in range(3)] + [(torch.randn(K, 4 * K, generator=g) * 0.3).to(d)]
+             for _ in range(2)]
+    ref = [ops.edge_mlp_bwd(ea, None, go, *w, need_dea=False)[1] for w in wsets]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(3):
+        out = []
+        for s, w in zip(streams, wsets):
+            with torch.cuda.stream(s):
+                out.append(ops.edge_mlp_bwd(ea, None, go, *w, need_dea=False)[1])
+        torch.cuda.synchronize()
+        for o, r in zip(out, ref):
+            for a, b in zip(o, r):
+                assert torch.equal(a, b)
+    keys = [k for k in ops._workspaces if k[0] == 0]
+    assert len({k[1] for k in keys}) >= 3          # default stream + the two side streams
+
+
+def test_ml3layer_without_learned_edges_ignores_extra_channels():
+    """with learnedge=False the reference reads edge_attr[:, :K] only (libs/spect_conv.py:76-80)."""
+    from gnn_matlang_b200.libs.spect_conv import ML3Layer
+    d = torch.device("cuda:0")
+    torch.manual_seed(0)
+    N, E, K = 300, 2000, 4
+    layer = ML3Layer(False, K, K, 10, 16, 4).to(d)
+    x = torch.randn(N, 10, device=d)
+    ei = torch.randint(0, N, (2, E), device=d)
+    ea = torch.randn(E, K + 3, device=d)
+    a = layer(x, ei, ea)
+    b = layer(x, ei, ea[:, :K].contiguous())
+    assert torch.equal(a, b)

@@ -6,9 +6,12 @@
 set -u
 cd "$(dirname "$0")/.."
 SEL='not large and not 100000 and not 190001 and not 65536 and not 150000'
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 \
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 7 \
     python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fused.py -q -x -k "$SEL"
 echo "memcheck exit code: $?"
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 \
-    python -m pytest tests/test_gpu_kernels.py -q -x -k "(edge_mlp or gemm_tn or segment_pool) and $SEL"
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 7 \
+    python -m pytest tests/test_gpu_model.py -q -x -k "(edge_mlp or segment_pool) and not 70000 and $SEL"
+echo "memcheck (edge MLP, both generations) exit code: $?"
+timeout 300 compute-sanitizer --tool racecheck --error-exitcode 7 \
+    python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -x -k "(edge_mlp or gemm_tn or segment_pool) and not 70000 and $SEL"
 echo "racecheck exit code: $?"
