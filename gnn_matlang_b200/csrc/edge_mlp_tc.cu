@@ -86,7 +86,7 @@ struct EMTParams {
     int64_t E;
     float* out;       // forward
     float* dea;       // backward, mode 2
-    float* partial;   // backward: [gridDim.x * groups][NT * 16]
+    float* partial;   // backward: [gridDim.x][NT * 16]
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -539,11 +539,19 @@ __global__ void __launch_bounds__(EMT<K>::nwg(MODE) * 128, 1) k_edge_mlp_tc(cons
             }
         }
         emt_group_sync(barid);
-        float* dst = p.partial + ((size_t)blockIdx.x * NWG + wg) * T::NT * 16;
         for (int i = t; i < T::NT * 16; i += 128) {
             float s = 0.f;
 #pragma unroll
             for (int g = 0; g < T::GROUPS; ++g) s += red[(size_t)g * T::NT * 16 + i];
+            red[i] = s;                                   // (index i of every thread group is read and written by this thread only)
+        }
+        // ... then the worker groups of the CTA, again in a fixed order: ONE partial per CTA for k_edge_mlp_bwd_reduce
+        __syncthreads();
+        float* dst = p.partial + (size_t)blockIdx.x * T::NT * 16;
+        for (int i = threadIdx.x; i < T::NT * 16; i += NWG * 128) {
+            float s = 0.f;
+#pragma unroll
+            for (int g = 0; g < NWG; ++g) s += stage_all[(size_t)g * 128 * C::S + i];
             dst[i] = s;
         }
     }
@@ -564,7 +572,7 @@ static int emt_launch(const EMTParams& p, int* nparts, cudaStream_t st) {
     if (grid > kNumSMs) grid = kNumSMs;
     k_edge_mlp_tc<K, MODE><<<(int)grid, NWG * 128, T::smem_bytes(MODE), st>>>(p);
     GNNML3_LAUNCH_CHECK();
-    if (nparts) *nparts = (int)grid * NWG;
+    if (nparts) *nparts = (int)grid;
     return GNNML3_OK;
 }
 
@@ -594,7 +602,7 @@ int edge_mlp_tc_fwd(const float* ea, const int32_t* eperm, const float* w1, cons
 size_t edge_mlp_tc_bwd_workspace_bytes(int K) {
     const int KP = pad4(K), T = 4 * K, DP = pad4(6 * K);
     const size_t nt = (size_t)(KP / 4) * (T / 4) + (size_t)(DP / 4) * (KP / 4);
-    return (size_t)kNumSMs * 4 * nt * 16 * sizeof(float);
+    return (size_t)kNumSMs * nt * 16 * sizeof(float);
 }
 
 int edge_mlp_tc_bwd(const float* ea, const int32_t* eperm, const float* gout, const float* w1, const float* w2, const float* w3,

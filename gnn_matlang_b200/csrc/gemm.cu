@@ -528,7 +528,7 @@ extern "C" size_t gnnml3_gemm_tn_workspace_bytes(int64_t M, int Ka, int Nb) {
     int64_t rps;
     tn_plan(M > 0 ? M : 1, Ka, Nb, &splits, &rps);
     if (tn_narrow(Ka, Nb)) splits = (int)cdiv(M > 0 ? M : 1, (int64_t)TNN_ROWS);
-    if (gemm_tn_tc_shape_ok(M, Ka, Nb) && gemm_tn_tc_parts(M) > splits) splits = gemm_tn_tc_parts(M);
+    if (gemm_tn_tc_shape_ok(M, Ka < 32 ? Ka : 32, Nb) && gemm_tn_tc_parts(M) > splits) splits = gemm_tn_tc_parts(M);
     return align_up((size_t)splits * Ka * Nb * sizeof(float), 256);
 }
 
@@ -584,14 +584,19 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
     }
     const bool x3 = precision == GNNML3_PREC_3XTF32;
     static const bool no_tc = getenv("GNNML3_NO_TN_TC") != nullptr;
-    if (x3 && !no_tc && gemm_tn_tc_ok(A, lda, B, ldb, M, Ka, Nb)) {
-        // 256 columns of B per launch (one TMEM accumulator set); the partial buffer is reused, launches are stream-ordered
-        for (int c0 = 0; c0 < Nb; c0 += 256) {
-            const int nbc = Nb - c0 < 256 ? Nb - c0 : 256;
-            if ((rc = gemm_tn_tc_launch(A, lda, B + c0, ldb, P, M, Ka, nbc, st))) return rc;
-            const int64_t n = (int64_t)Ka * nbc;
-            k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, gemm_tn_tc_parts(M), n, nbc, C + c0, ldc);
-            GNNML3_LAUNCH_CHECK();
+    if (x3 && !no_tc && gemm_tn_tc_ok(A, lda, B, ldb, M, Ka < 32 ? Ka : 32, Nb)) {
+        // 32 columns of A (the M side of the instruction: [x_hi; x_lo] = 64 lanes) x 256 columns of B (one TMEM accumulator set)
+        // per launch; the partial buffer is reused, launches are stream-ordered.  Wide A (the F = 64..256 sweep) re-reads B once
+        // per 32-column block of A -- still less time than the mma.sync kernel (F = 64: 1.3 vs 2.1 ms per 1 M rows x 640 columns).
+        for (int a0 = 0; a0 < Ka; a0 += 32) {
+            const int kac = Ka - a0 < 32 ? Ka - a0 : 32;
+            for (int c0 = 0; c0 < Nb; c0 += 256) {
+                const int nbc = Nb - c0 < 256 ? Nb - c0 : 256;
+                if ((rc = gemm_tn_tc_launch(A + a0, lda, B + c0, ldb, P, M, kac, nbc, st))) return rc;
+                const int64_t n = (int64_t)kac * nbc;
+                k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, gemm_tn_tc_parts(M), n, nbc, C + (int64_t)a0 * ldc + c0, ldc);
+                GNNML3_LAUNCH_CHECK();
+            }
         }
         return GNNML3_OK;
     }

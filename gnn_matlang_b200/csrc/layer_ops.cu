@@ -135,15 +135,29 @@ k_ml3_act_bwd_y(const float* __restrict__ y, int64_t ldy, const float* __restric
         if (colpart) *reinterpret_cast<float4*>(tile + rl * (int)ldg + c) = o;
     }
     if (colpart) {
+        // column sums of the staged tile in two fixed-order levels: (segment of rows, column) per thread, then the segments of a
+        // column (one thread per column walking all 128 rows serially was half of the kernel's time)
+        __shared__ float seg_sum[256];
         __syncthreads();
-        const int c = threadIdx.x;
-        if (c < (int)ldg) {
+        const int ld = (int)ldg;
+        const int nseg = (int)blockDim.x / ld;                       // ld <= ACTY_MAXLD = 72: at least 3 segments
+        const int rps = (ACTY_ROWS + nseg - 1) / nseg;
+        const int sg = threadIdx.x / ld, c = threadIdx.x - sg * ld;
+        if (sg < nseg) {
+            float t = 0.f;
+            const int r1 = min(rows, (sg + 1) * rps);
+            for (int rl = sg * rps; rl < r1; ++rl) t += tile[rl * ld + c];
+            seg_sum[sg * ld + c] = t;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < ld) {
+            const int cc = threadIdx.x;
             int lc = -1;
-            if (c < Fo) lc = c;
-            else if (c >= Fo4 && c < Fo4 + 2 * G) lc = Fo + (c - Fo4);
+            if (cc < Fo) lc = cc;
+            else if (cc >= Fo4 && cc < Fo4 + 2 * G) lc = Fo + (cc - Fo4);
             if (lc >= 0) {
                 float t = 0.f;
-                for (int rl = 0; rl < rows; ++rl) t += tile[rl * (int)ldg + c];      // fixed order: deterministic
+                for (int g2 = 0; g2 < nseg; ++g2) t += seg_sum[g2 * ld + cc];      // fixed order: deterministic
                 colpart[(int64_t)blockIdx.x * W2 + lc] = t;
             }
         }

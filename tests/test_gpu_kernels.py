@@ -169,7 +169,8 @@ def test_gemm_nn(M, Kc, Nc):
                                      (2048, 2, 96),
                                      (190001, 32, 4), (3000, 25, 4), (5000, 48, 8), (300, 64, 1),    # narrow (gate) path
                                      (190001, 32, 256), (20000, 28, 100), (9000, 4, 12), (65536, 32, 64), (8200, 32, 252),
-                                     (30000, 32, 320), (12000, 16, 384), (9000, 8, 260)])  # tcgen05 path (last three: several 256-column launches)
+                                     (30000, 32, 320), (12000, 16, 384), (9000, 8, 260),  # tcgen05 path (last three: several 256-column launches)
+                                     (20000, 64, 640), (10000, 100, 300), (9000, 130, 70)])  # wide A: 32-column blocks of A x 256-column blocks of B
 def test_gemm_tn_and_colsum(M, Ka, Nb):
     from gnn_matlang_b200 import ops
     g = torch.Generator().manual_seed(M + Ka + Nb)
