@@ -33,7 +33,7 @@ WORKLOADS = {
     "exp": ("exp", "exp", "bce", 4096, "exp_classify.py GNNML3 (3 x ML3Layer 32||16, K=6, mean-pool, BCE-sum, Adam 1e-3), "
             "SpectralDesign(recfield=1, dv=2, nfreq=5, adddegree) rebuilt on the GPU every step", 50),
 }
-LAUNCH_PROFILE = os.path.join(ROOT, "profiles", "r02_ncu_launches_zinc_one_step.csv")
+LAUNCH_PROFILE = os.path.join(ROOT, "profiles", "r02_ncu_launches_zinc_one_step_final.csv")
 
 
 def parse():
@@ -558,7 +558,11 @@ def main():
                     "algorithmic_bytes_per_launch": sp_bytes / len(recs),
                     "measured_in": "%d steps of the same training step enqueued launch by launch right after the timed region (CUDA "
                                    "events on the launching stream inside gnnml3_fused_agg_proj)" % nprof,
-                    "note": "FP32 FMA issue of the aggregation (about 60 % SIMD efficiency over ragged rows) + per-tile hand-off, see DESIGN.md section 4"}
+                    "traffic_note": "mean of 4 forward launches (66 MB each: x / y stay in L2 between kernels) and 3 dx launches (264 MB each: they also "
+                                    "write the 190 MB aggregate side output the weight-gradient contraction reads, which is not credited "
+                                    "as algorithmic bytes); no re-reads",
+                    "note": "latency / hand-off bound, not bandwidth bound: FP32 FMA issue of the aggregation (61 % of the lanes active over ragged "
+                            "rows) + per-pass fixed cost (set-up, residuals, tcgen05.st hand-off), see DESIGN.md section 4.1"}
 
     # ---- end to end: pinned host batches in the compact wire format -> H2D on a copy stream (one step ahead) -> rebuilt on the
     #      device -> written into the captured buffers -> graph replay; D2H of every step's loss inside the timed region

@@ -5,10 +5,14 @@
 * ``read_exp_pickle`` -- ``dataset/EXP/raw/GRAPHSAT.pkl`` (reference: ``libs/utils.py:440-442``: a pickled list of PyG
   ``Data`` objects; read here without torch_geometric by mapping the pickled classes to a plain record)
 
-Both return a list of ``dict(x, edge_index, y)`` records (numpy / torch on the host), the input ``SpectralDesign`` and
+* ``read_mat``      -- the MATLAB files of the other GNNML3 scripts: ``Zinc.mat`` (``libs/utils.py:240-261``: atom type |
+  degree code one-hot features, nmax 37), ``randomgraph.mat`` of the counting task (``:386-413``: the five substructure
+  counts recomputed from the adjacency exactly as the reference does), and the TU files that do ship with the reference,
+  ``enzymes.mat`` / ``proteins.mat`` (``:93-112, 146-165``: first three feature columns unless ``contfeat``), ``ptc.mat``
+  (``:46-61``), ``mutag.mat`` (``:195-211``: labels mapped from {-1, 1} to {0, 1})
+
+All return a list of ``dict(x, edge_index, y)`` records (numpy on the host), the input ``SpectralDesign`` and
 ``batch.collate`` take.  Host-side parsing only: integer work, bit-exact by construction; nothing here touches the GPU.
-The ``.mat`` schemas of ZINC / counting (``libs/utils.py:240-261, 386-413``) are not implemented: neither file ships with the
-reference.
 """
 import io
 import pickle
@@ -16,7 +20,7 @@ import pickle
 import numpy as np
 import torch
 
-__all__ = ["read_graph6", "read_exp_pickle"]
+__all__ = ["read_graph6", "read_exp_pickle", "read_mat"]
 
 
 def _g6_graph(line):
@@ -97,4 +101,69 @@ def read_exp_pickle(path_or_bytes):
         ei = ei if isinstance(ei, torch.Tensor) else torch.as_tensor(ei)
         out.append(dict(x=x.reshape(x.shape[0], -1).to(torch.int64).numpy(), edge_index=ei.to(torch.int64).numpy(),
                         y=int(torch.as_tensor(y).reshape(-1)[0]) if y is not None else 0))
+    return out
+
+
+def _edges_of(A):
+    """``np.where(A > 0)`` of a dense (or scipy-sparse) adjacency: row-major order = sorted by (source, target)."""
+    A = A.toarray() if hasattr(A, "toarray") else np.asarray(A)
+    r, c = np.where(A > 0)
+    return A, np.vstack((r, c)).astype(np.int64)
+
+
+def _comb3(d):
+    d = int(d)
+    return d * (d - 1) * (d - 2) // 6 if d >= 3 else 0
+
+
+def read_mat(path, kind, contfeat=False):
+    """Records of one of the reference's MATLAB datasets (``scipy.io.loadmat``); ``kind`` in
+    {"zinc", "counting", "enzymes", "proteins", "ptc", "mutag"}.  Follows the ``process()`` of the reference's dataset class line
+    by line (see the module docstring for the line ranges); ``y`` keeps the reference's dtype (int64 class ids, float32 for
+    ZINC / mutag, float64 counts for the counting task)."""
+    import scipy.io as sio
+    a = sio.loadmat(path)
+    out = []
+    if kind == "zinc":                                   # Zinc12KDataset.process
+        F, E, Y = a["F"][0], a["E"][0], a["Y"]
+        ntype, maxdeg = 21, 4
+        for i in range(len(E)):
+            A, ei = _edges_of(E[i])
+            n = A.shape[0]
+            x = np.zeros((n, ntype + maxdeg), np.float32)
+            deg = (A > 0).sum(1)
+            codes = np.asarray(F[i][0]).reshape(-1)
+            for j in range(codes.shape[0]):
+                x[j, int(codes[j])] = 1                  # atom code
+                x[j, -int(deg[j])] = 1                   # degree code (from the end; degree 0 lands on column 0 as in the reference)
+            out.append(dict(x=x, edge_index=ei, y=np.asarray(Y[i, :])))
+    elif kind == "counting":                             # GraphCountDataset.process
+        As = a["A"][0]
+        for i in range(len(As)):
+            A, ei = _edges_of(As[i])
+            A = A.astype(np.float64)
+            A2 = A.dot(A)
+            A3 = A2.dot(A)
+            tri = np.trace(A3) / 6
+            tailed = ((np.diag(A3) / 2) * (A.sum(0) - 2)).sum()
+            cyc4 = 1 / 8 * (np.trace(A3.dot(A)) + np.trace(A2) - 2 * A2.sum())
+            cus = A.dot(np.diag(np.exp(-A.dot(A).sum(1)))).dot(A).sum()
+            star = sum(_comb3(d) for d in A.sum(0))
+            out.append(dict(x=np.ones((A.shape[0], 1), np.float32), edge_index=ei, y=np.array([[tri, tailed, star, cyc4, cus]])))
+    elif kind in ("enzymes", "proteins", "ptc"):
+        As, F = a["A"][0], a["F"][0]
+        Y = a["Y"][0].astype(np.int64) if kind == "enzymes" else a["Y"].astype(np.int64)[:, 0]
+        for i in range(len(As)):
+            _, ei = _edges_of(As[i])
+            f = np.asarray(F[i])
+            x = (f if (contfeat or kind == "ptc") else f[:, 0:3]).astype(np.float32)
+            out.append(dict(x=x, edge_index=ei, y=np.array([Y[i]], np.int64)))
+    elif kind == "mutag":
+        As, F = a["A"][0], a["F"][0]
+        Y = ((a["y"] + 1) // 2).astype(np.float32)
+        for i in range(len(As)):
+            _, ei = _edges_of(As[i])
+            out.append(dict(x=np.asarray(F[i]).astype(np.float32), edge_index=ei, y=Y[i].astype(np.float32)))
+    else:
+        raise ValueError("read_mat: unknown kind %r" % (kind,))
     return out

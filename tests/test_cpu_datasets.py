@@ -99,3 +99,79 @@ def test_read_exp_pickle_matches_the_committed_fixture():
         assert np.array_equal(e[i]["x"].reshape(-1), z["x"][xo[i]:xo[i + 1]])
         assert np.array_equal(e[i]["edge_index"], z["edge_index"][:, eo[i]:eo[i + 1]])
         assert e[i]["y"] == int(z["y"][i])
+
+
+def test_read_mat_zinc_and_counting_schemas(tmp_path):
+    """Synthetic files in the schemas of libs/utils.py:240-261 (Zinc.mat) and :386-413 (randomgraph.mat); expected values from a
+    direct restatement of those lines."""
+    import scipy.io as sio
+    from scipy.special import comb
+    from gnn_matlang_b200.datasets import read_mat
+    rng = np.random.default_rng(0)
+    graphs = []
+    for n in (5, 9, 23):
+        A = np.triu((rng.random((n, n)) < 0.3).astype(np.uint8), 1)
+        A = A + A.T
+        graphs.append(A)
+    E = np.empty((1, len(graphs)), dtype=object)
+    F = np.empty((1, len(graphs)), dtype=object)
+    for i, A in enumerate(graphs):
+        A4 = np.minimum(A, 1) * (A.sum(1, keepdims=True) <= 4)          # keep degrees <= 4 like molecules
+        A4 = np.minimum(A4, A4.T)
+        graphs[i] = A4
+        E[0, i] = A4
+        F[0, i] = np.array([rng.integers(0, 21, A4.shape[0])])
+    Y = rng.normal(size=(len(graphs), 1))
+    sio.savemat(str(tmp_path / "Zinc.mat"), {"E": E, "F": F, "Y": Y})
+    recs = read_mat(str(tmp_path / "Zinc.mat"), "zinc")
+    assert len(recs) == 3
+    for i, r in enumerate(recs):
+        A = graphs[i]
+        ref_ei = np.vstack(np.where(A > 0))
+        assert np.array_equal(r["edge_index"], ref_ei) and r["edge_index"].dtype == np.int64
+        x = np.zeros((A.shape[0], 25), np.float32)
+        deg = (A > 0).sum(1)
+        for j in range(A.shape[0]):
+            x[j, F[0, i][0][j]] = 1
+            x[j, -int(deg[j])] = 1
+        assert np.array_equal(r["x"], x) and np.allclose(r["y"], Y[i, :])
+    Ac = np.empty((1, len(graphs)), dtype=object)
+    for i, A in enumerate(graphs):
+        Ac[0, i] = A.astype(np.float64)
+    sio.savemat(str(tmp_path / "randomgraph.mat"), {"A": Ac, "F": np.zeros((3, 5))})
+    recs = read_mat(str(tmp_path / "randomgraph.mat"), "counting")
+    for i, r in enumerate(recs):
+        a = graphs[i].astype(np.float64)
+        A2 = a.dot(a); A3 = A2.dot(a)
+        tri = np.trace(A3) / 6
+        tailed = ((np.diag(A3) / 2) * (a.sum(0) - 2)).sum()
+        cyc4 = 1 / 8 * (np.trace(A3.dot(a)) + np.trace(A2) - 2 * A2.sum())
+        cus = a.dot(np.diag(np.exp(-a.dot(a).sum(1)))).dot(a).sum()
+        star = sum(comb(int(d), 3) for d in a.sum(0))
+        assert np.allclose(r["y"], [[tri, tailed, star, cyc4, cus]], rtol=0, atol=1e-12)
+        assert r["x"].shape == (a.shape[0], 1) and float(r["x"].min()) == 1.0
+        assert np.array_equal(r["edge_index"], np.vstack(np.where(a > 0)))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/dataset/enzymes/raw/enzymes.mat"), reason="reference checkout not present")
+@pytest.mark.parametrize("kind,rel,count,nfeat", [("enzymes", "enzymes/raw/enzymes.mat", 600, 3), ("proteins", "proteins/raw/proteins.mat", 1113, 3),
+                                                  ("ptc", "PTC/raw/ptc.mat", 344, None), ("mutag", "mutag/raw/mutag.mat", 188, None)])
+def test_read_mat_tu_files_shipped_with_the_reference(kind, rel, count, nfeat):
+    """The TU files that ship with the reference, against a restatement of the dataset classes' process() lines
+    (libs/utils.py:46-61, 93-112, 146-165, 195-211)."""
+    import scipy.io as sio
+    from gnn_matlang_b200.datasets import read_mat
+    path = os.path.join("/root/reference/dataset", rel)
+    recs = read_mat(path, kind)
+    a = sio.loadmat(path)
+    assert len(recs) == count
+    A, F = a["A"][0], a["F"][0]
+    for i in (0, 1, count // 2, count - 1):
+        Ai = A[i].toarray() if hasattr(A[i], "toarray") else A[i]
+        assert np.array_equal(recs[i]["edge_index"], np.vstack(np.where(Ai > 0)))
+        f = np.asarray(F[i])
+        assert np.array_equal(recs[i]["x"], (f[:, 0:3] if nfeat else f).astype(np.float32))
+    if kind == "mutag":
+        assert set(float(r["y"][0]) for r in recs) == {0.0, 1.0}
+    elif kind == "enzymes":
+        assert sorted(set(int(r["y"][0]) for r in recs)) == sorted(set(int(v) for v in a["Y"][0]))

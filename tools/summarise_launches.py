@@ -3,7 +3,7 @@ totals for ONE training step (the last complete step of the capture).
 
 usage: python tools/summarise_launches.py raw.csv n_steps_total > one_step.csv
        python tools/summarise_launches.py raw.csv --marker k_csr_hist > one_step.csv     (a step starts at every launch of the
-                                                       marker kernel: the CSR build opens each training step; takes the last step)
+                                                       marker kernel: the CSR build opens each training step; takes the last complete step)
 """
 import collections
 import csv
@@ -24,7 +24,8 @@ def main():
     rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
     if sys.argv[2] == "--marker":
         starts = [i for i, r in enumerate(rows) if sys.argv[3] in r[4]]
-        last = rows[starts[-1]:]
+        # the capture may end in the middle of a step (-c N): take the last COMPLETE step when there is one
+        last = rows[starts[-2]:starts[-1]] if len(starts) >= 2 else rows[starts[-1]:]
     else:
         steps = int(sys.argv[2])
         per = len(rows) // steps
