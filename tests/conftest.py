@@ -34,3 +34,15 @@ def golden_conv():
 @pytest.fixture(scope="session")
 def golden_model():
     return load_npz("graph8c_model.npz")[0]
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Share of compared entries that pass the plain element-wise rtol (without the rtol * max|ref| term of assert_close)."""
+    try:
+        import test_gpu_kernels
+        st = test_gpu_kernels.PURE_RTOL_STATS
+    except Exception:
+        return
+    if st["entries"]:
+        terminalreporter.write_line("assert_close: %d calls, %d entries compared, %.4f %% within the plain element-wise rtol"
+                                    % (st["calls"], st["entries"], 100.0 * st["within_pure_rtol"] / st["entries"]))
