@@ -572,14 +572,16 @@ def main():
         for hb in host_ring:
             feeder.compact(hb)                  # wire-format conversion = data preparation, like collation: outside the timed region
         if use_graph:
-            def e2e_step(b):
-                trainer.load_unpadded(b)
+            def e2e_step(cb):                   # wire format -> captured buffers (two library launches), graph replay
+                trainer.load_compact(cb)
                 return trainer.step()
+            fetch = feeder.get_compact
         else:
             e2e_step = trainer.step
+            fetch = feeder.get
         feeder.prefetch(host_ring[0])
         for i in range(3):
-            b = feeder.get()
+            b = fetch()
             feeder.prefetch(host_ring[(i + 1) % args.ring])
             float(e2e_step(b).item())
         barrier()
@@ -590,7 +592,7 @@ def main():
         loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
         lv = float("nan")
         for i in range(args.steps):
-            b = feeder.get()
+            b = fetch()
             feeder.prefetch(host_ring[(i + 4) % args.ring])
             lt = e2e_step(b)
             loss_host[i & 1].copy_(lt.reshape(1), non_blocking=True)      # device -> host read of the step's loss
@@ -621,12 +623,19 @@ def main():
                 if not use_graph or (pool.n[idx].sum() < Np and Ep - 8 * (Np - pool.n[idx].sum()) <= pool.e[idx].sum() <= Ep):
                     break
             idx_host.append(torch.from_numpy(idx.astype(np.int64)).pin_memory())
+        if use_graph:
+            def ds_step(ix):                    # id list -> captured buffers, collated on the device (two library launches)
+                trainer.load_from_dataset(dds, ix)
+                return trainer.step()
+        else:
+            def ds_step(ix):
+                return trainer.step(dds.collate(ix))
         for i in range(3):
-            float(e2e_step(dds.collate(idx_host[i % args.ring])).item())
+            float(ds_step(idx_host[i % args.ring]).item())
         barrier()
         e0.record()
         for i in range(args.steps):
-            lt = e2e_step(dds.collate(idx_host[i % args.ring]))
+            lt = ds_step(idx_host[i % args.ring])
             loss_host[i & 1].copy_(lt.reshape(1), non_blocking=True)
             loss_ev[i & 1].record()
             if i > 0:

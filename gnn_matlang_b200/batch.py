@@ -100,7 +100,7 @@ class CompactBatch(object):
         if len(eg) and np.any(np.diff(eg) < 0):
             raise ValueError("edge_index2 is not grouped by graph")
         dt = np.uint8 if (n.max() if len(n) else 0) <= 256 else np.int16 if n.max() <= 32768 else np.int32
-        kw = dict(n=torch.from_numpy(n.astype(np.int32)), e=torch.from_numpy(e.astype(np.int32)), el=torch.from_numpy(loc.astype(dt)),
+        kw = dict(n=torch.from_numpy(n.astype(np.int32)), e=torch.from_numpy(e.astype(np.int32)), el=torch.from_numpy(np.ascontiguousarray(loc.astype(dt))),
                   ea=b.edge_attr2, y=getattr(b, "y", None), num_graphs=len(n), widths=None, x=None, xc=None)
         x = b.x.numpy()
         if onehot_widths is not None:
@@ -134,31 +134,32 @@ class CompactBatch(object):
             out.__dict__[k] = v.to(device, non_blocking=non_blocking)
         return out
 
+    def _out(self, Np, Ep, padded):
+        dev = self.n.device
+        F = sum(self.widths) if self.xc is not None else self.x.size(1)
+        B = self.num_graphs
+        return Batch(x=torch.empty(Np, F, dtype=torch.float32, device=dev), edge_index2=torch.empty(2, Ep, dtype=torch.int64, device=dev),
+                     edge_attr2=torch.empty(Ep, self.ea.size(1), dtype=torch.float32, device=dev),
+                     batch=torch.empty(Np, dtype=torch.int64, device=dev),
+                     graph_ptr=torch.empty(B + (2 if padded else 1), dtype=torch.int32, device=dev), num_graphs=B)
+
+    def expand_into(self, out):
+        """Device ``CompactBatch`` -> the preallocated device ``Batch`` ``out`` (its tensors may be larger than the batch: the rest
+        receives the neutral padding of ``train.pad_batch``).  Two library launches (``gnnml3_collate``), no host sync; integer
+        work, bit-exact with host ``collate``."""
+        from . import ops
+        ops.collate_device(self.n, self.e, self.el, self.ea, self.num_graphs, out, xc=self.xc, widths=self.widths, x=self.x)
+        if self.y is not None and getattr(out, "y", None) is not None and out.y is not self.y:
+            out.y.copy_(self.y.reshape(out.y.shape), non_blocking=True)
+        return out
+
     def expand(self):
         """Device ``CompactBatch`` -> device ``Batch`` with the reference's attributes (``x``, ``edge_index2`` int64 global ids,
         ``edge_attr2``, ``batch`` int64, ``y``) + ``graph_ptr``; integer work, bit-exact with host ``collate``."""
-        dev = self.n.device
-        B = self.num_graphs
-        n64, e64 = self.n.long(), self.e.long()
-        gp = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(n64, 0, out=gp[1:])
         N, E = (self.xc if self.xc is not None else self.x).size(0), self.el.size(1)
-        ar = torch.arange(B, device=dev)
-        batch = torch.repeat_interleave(ar, n64, output_size=N)
-        eoff = torch.repeat_interleave(gp[:-1], e64, output_size=E)
-        ei = self.el.long() + eoff.unsqueeze(0)
-        if self.xc is not None:
-            F = sum(self.widths)
-            x = torch.zeros(N, F, dtype=torch.float32, device=dev)
-            off = 0
-            for c, w in enumerate(self.widths):
-                x.scatter_(1, (self.xc[:, c].long() + off).unsqueeze(1), 1.0)
-                off += w
-        else:
-            x = self.x
-        gp32 = gp.to(torch.int32)
-        out = Batch(x=x, edge_index2=ei, edge_attr2=self.ea, batch=batch, num_graphs=B, graph_ptr=gp32)
+        out = self._out(N, E, False)
         if self.y is not None:
             out.y = self.y
-        out.batch._gnnml3_ptr = (out.batch._version, gp32)
+        self.expand_into(out)
+        out.batch._gnnml3_ptr = (out.batch._version, out.graph_ptr)
         return out

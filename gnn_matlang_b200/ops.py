@@ -544,6 +544,53 @@ def ml3layer_backward(plan, x, ea_s, ea2, ws4, wconv, gates_w, y, aux, gy, need_
     return (dx[:, :Fi] if need_dx else None), dea, dws, dwc, dbc, dw11, db11, dw12, db12
 
 
+def collate_device(n, e, el, ea, B, out, idx=None, node_off=None, edge_off=None, xc=None, widths=None, x=None):
+    """Batch B per-graph records on the device (gnnml3_collate) into the tensors of ``out`` (a ``Batch`` whose ``x [Np, F]``,
+    ``edge_index2 [2, Ep]`` int64, ``edge_attr2 [Ep, K]``, ``batch [Np]`` int64 and ``graph_ptr`` int32 are preallocated; rows
+    beyond the batch's nodes / entries get the neutral padding of a captured step).  Records: ``n`` / ``e`` int32 sizes,
+    ``el [2, *]`` graph-local ids (uint8 / int16 / int32 / int64), ``ea [*, K]``, features ``x [*, F]`` or uint8 class codes
+    ``xc [*, C]`` + ``widths``; ``idx`` (int64 graph ids) with ``node_off`` / ``edge_off`` (int64) select records of a resident
+    pool, None = the records are the batch itself in order."""
+    import ctypes
+    lib = _lib.load()
+    dev = ea.device
+    if el.is_cuda and not el.is_contiguous():
+        el = el.contiguous()
+    for name, t in (("n", n), ("e", e), ("el", el), ("ea", ea), ("out.x", out.x), ("out.edge_index2", out.edge_index2),
+                    ("out.edge_attr2", out.edge_attr2), ("out.batch", out.batch), ("out.graph_ptr", out.graph_ptr)):
+        if not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("collate_device: %s must be a contiguous CUDA tensor (no CPU fallback)" % name)
+    if n.dtype != torch.int32 or e.dtype != torch.int32 or out.edge_index2.dtype != torch.int64 or out.batch.dtype != torch.int64 \
+            or out.graph_ptr.dtype != torch.int32 or ea.dtype != torch.float32 or out.x.dtype != torch.float32:
+        raise RuntimeError("collate_device: unexpected dtype")
+    el_bytes = el.element_size()
+    if el.dtype not in (torch.uint8, torch.int16, torch.int32, torch.int64):
+        raise RuntimeError("collate_device: el must be uint8 / int16 / int32 / int64")
+    Np, F = out.x.shape
+    Ep, K = out.edge_attr2.shape
+    if out.edge_index2.size(1) != Ep or out.batch.numel() != Np or out.graph_ptr.numel() < B + 1 or ea.size(1) != K:
+        raise RuntimeError("collate_device: output shapes do not match")
+    wh = None
+    C = 0
+    if xc is not None:
+        C = xc.size(1)
+        wh = (ctypes.c_int32 * C)(*[int(w) for w in widths])
+        if xc.dtype != torch.uint8 or not xc.is_contiguous():
+            raise RuntimeError("collate_device: xc must be a contiguous uint8 tensor")
+    elif x is None or x.dtype != torch.float32 or not x.is_contiguous() or x.size(1) != F:
+        raise RuntimeError("collate_device: x [*, F] float32 or xc + widths must be given")
+    for t in (idx, node_off, edge_off):
+        if t is not None and (t.dtype != torch.int64 or not t.is_cuda or not t.is_contiguous()):
+            raise RuntimeError("collate_device: idx / node_off / edge_off must be contiguous int64 CUDA tensors")
+    ws = _ws(dev, lib.gnnml3_collate_workspace_bytes(int(B)), tag="collate")
+    with _on(dev):
+        _lib.check(lib.gnnml3_collate(_lib.ptr(idx), _lib.ptr(n), _lib.ptr(e), _lib.ptr(node_off), _lib.ptr(edge_off), _lib.ptr(xc), C,
+                                      wh, _lib.ptr(x), F, _lib.ptr(el), el_bytes, el.size(1), _lib.ptr(ea), K, int(B), Np, Ep,
+                                      _lib.ptr(out.x), _lib.ptr(out.edge_index2), _lib.ptr(out.edge_attr2), _lib.ptr(out.batch),
+                                      _lib.ptr(out.graph_ptr), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_collate")
+    return out
+
+
 def segment_pool_fwd(x, graph_ptr, mean):
     lib = _lib.load()
     x = _f32c(x, "x")

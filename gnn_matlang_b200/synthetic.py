@@ -259,31 +259,41 @@ class DeviceDataset(object):
         self.n_h, self.e_h = pool.n, pool.e                      # host copies: batch sizes are known without a device round trip
         t = lambda a, dt=None: torch.as_tensor(a if dt is None else a.astype(dt)).to(device)
         self.n, self.e = t(pool.n), t(pool.e)
+        self.n32, self.e32 = self.n.to(torch.int32), self.e.to(torch.int32)
         self.node_off, self.edge_off = t(pool.node_off), t(pool.edge_off)
         self.x = t(pool.x)
         self.el = t(pool.ei2)                                    # support coordinates, node ids local to their graph
         self.ea = t(pool.ea2)
         self.y = t(pool.y)
 
-    def collate(self, idx_host):
-        """``idx_host``: int64/int32 numpy array or pinned CPU tensor of graph ids -> device ``Batch``."""
+    def _idx(self, idx_host):
         idx_np = idx_host.numpy() if isinstance(idx_host, torch.Tensor) else np.asarray(idx_host)
-        N, E = int(self.n_h[idx_np].sum()), int(self.e_h[idx_np].sum())
         idx = (idx_host if isinstance(idx_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(idx_np))).to(
             self.device, non_blocking=True).long()
+        return idx_np, idx
+
+    def collate_into(self, idx_host, out):
+        """Graph ids (int64 numpy array or pinned CPU tensor) -> the preallocated device ``Batch`` ``out`` (larger tensors get the
+        neutral padding of ``train.pad_batch``): ONE host -> device copy of the id list and two library launches."""
+        from . import ops
+        _, idx = self._idx(idx_host)
+        ops.collate_device(self.n32, self.e32, self.el, self.ea, idx.numel(), out, idx=idx, node_off=self.node_off, edge_off=self.edge_off,
+                           x=self.x)
+        if getattr(out, "y", None) is not None:
+            out.y.copy_(self.y[idx].reshape(out.y.shape))
+        return out
+
+    def collate(self, idx_host):
+        """``idx_host``: int64/int32 numpy array or pinned CPU tensor of graph ids -> device ``Batch`` (exact sizes)."""
+        idx_np, idx = self._idx(idx_host)
+        N, E = int(self.n_h[idx_np].sum()), int(self.e_h[idx_np].sum())
         dev = self.device
         B = idx.numel()
-        n, e = self.n[idx], self.e[idx]
-        gp = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(n, 0, out=gp[1:])
-        ep = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(e, 0, out=ep[1:])
-        nsel = torch.repeat_interleave(self.node_off[idx] - gp[:-1], n, output_size=N) + torch.arange(N, device=dev)
-        esel = torch.repeat_interleave(self.edge_off[idx] - ep[:-1], e, output_size=E) + torch.arange(E, device=dev)
-        ei = self.el[:, esel] + torch.repeat_interleave(gp[:-1], e, output_size=E).unsqueeze(0)
-        batch = torch.repeat_interleave(torch.arange(B, device=dev), n, output_size=N)
-        gp32 = gp.to(torch.int32)
-        out = Batch(x=self.x[nsel], edge_index2=ei, edge_attr2=self.ea[esel], batch=batch, num_graphs=B, graph_ptr=gp32,
-                    y=self.y[idx].reshape(-1, 1))
-        out.batch._gnnml3_ptr = (out.batch._version, gp32)
+        out = Batch(x=torch.empty(N, self.x.size(1), dtype=torch.float32, device=dev), edge_index2=torch.empty(2, E, dtype=torch.int64, device=dev),
+                    edge_attr2=torch.empty(E, self.ea.size(1), dtype=torch.float32, device=dev), batch=torch.empty(N, dtype=torch.int64, device=dev),
+                    graph_ptr=torch.empty(B + 1, dtype=torch.int32, device=dev), num_graphs=B)
+        from . import ops
+        ops.collate_device(self.n32, self.e32, self.el, self.ea, B, out, idx=idx, node_off=self.node_off, edge_off=self.edge_off, x=self.x)
+        out.y = self.y[idx].reshape(-1, 1)
+        out.batch._gnnml3_ptr = (out.batch._version, out.graph_ptr)
         return out

@@ -95,13 +95,17 @@ class HostFeeder(object):
         ev.record(self.copy_stream)
         self._next = (b, ev)
 
-    def get(self):
+    def get_compact(self):
+        """The prefetched batch, still in the wire format, on the device (ordered behind its copy on the current stream)."""
         b, ev = self._next
         torch.cuda.current_stream().wait_event(ev)
         for v in b._tensors().values():
             v.record_stream(torch.cuda.current_stream())
         self._next = None
-        return b.expand()
+        return b
+
+    def get(self):
+        return self.get_compact().expand()
 
 
 def pad_batch(hb, n_nodes, n_entries):
@@ -241,6 +245,19 @@ class GraphedTrainer(object):
         st.graph_ptr[:self.real + 1].copy_(b.graph_ptr, non_blocking=True)
         st.graph_ptr[self.real + 1:].fill_(Np)
         st.y.copy_(b.y, non_blocking=True)
+
+    def load_compact(self, cb):
+        """Device ``CompactBatch`` (wire format) -> the captured input buffers, padding included: two library launches
+        (``gnnml3_collate``) + the label copy, instead of ~20 index kernels of ``expand`` and ~12 copies of ``load_unpadded``."""
+        st = self.static
+        N = (cb.xc if cb.xc is not None else cb.x).size(0)
+        if N >= st.x.size(0) or cb.el.size(1) > st.edge_index2.size(1) or cb.num_graphs != self.real:
+            raise ValueError("batch does not fit the captured shapes")
+        cb.expand_into(st)
+
+    def load_from_dataset(self, dataset, idx_host):
+        """Graph ids -> the captured input buffers, collated on the device from an HBM-resident ``DeviceDataset``."""
+        dataset.collate_into(idx_host, self.static)
 
     def step(self, batch=None):
         """One optimisation step; returns the (device, captured) loss tensor -- valid until the next step."""

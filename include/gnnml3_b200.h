@@ -292,6 +292,25 @@ GNNML3_API int gnnml3_gemm_nn_tc(const float* A, int64_t lda, const float* B, in
                       int64_t ldc, int64_t M, int Nc, int Kc, int epilogue, int chunk_kblocks, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Batching on the device (collate.cu): per-graph records -> one disjoint-union batch with the reference's attributes -- the
+ * semantics of PyG's Batch.from_data_list for the fields GNNML3 reads (DataLoader at graph8c.py:18, Zinc12k.py:20-22,
+ * exp_classify.py:19-21, counting.py:29-31).  The records are rows of tables in device memory: n / e (nodes / support entries
+ * per record), node_off / edge_off (first row of a record in x|xc and el|ea; NULL = the records are laid out in batch order),
+ * idx (the B records to batch, NULL = records 0..B-1).  Features are x [*, F] or, for concatenated one-hot blocks, uint8 class
+ * codes xc [*, C] with block widths (host array, sum = F).  el [2, el_stride] holds graph-local (src, dst) ids in el_bytes-wide
+ * integers.  Outputs: x [Np, F], edge_index2 [2, Ep] (int64, global ids), edge_attr2 [Ep, K], batch [Np] (int64),
+ * graph_ptr [B + 1] (int32; one more entry = Np when Np exceeds the batch's node count).  Rows beyond the batch's nodes /
+ * entries receive the neutral padding of a captured step: isolated zero-feature nodes forming one dummy graph B, all-zero
+ * self-loop entries spread over them.  Integer work, bit-exact with the host collation.  Two launches, no host sync.
+ * --------------------------------------------------------------------------------------------------- */
+GNNML3_API size_t gnnml3_collate_workspace_bytes(int B);
+GNNML3_API int gnnml3_collate(const int64_t* idx, const int32_t* n, const int32_t* e, const int64_t* node_off, const int64_t* edge_off,
+                   const uint8_t* xc, int C, const int32_t* widths_host, const float* x, int F, const void* el, int el_bytes,
+                   int64_t el_stride, const float* ea, int K, int B, int64_t Np, int64_t Ep, float* out_x,
+                   int64_t* out_edge_index, float* out_edge_attr, int64_t* out_batch, int32_t* out_graph_ptr,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,3 +82,31 @@ def test_captured_step_equals_eager_step_and_padding_is_neutral():
         assert abs(l1 - l2) <= 2e-5 * abs(l1), (i, l1, l2)
     for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         assert torch.allclose(a, b, rtol=0, atol=2e-6), k
+
+
+@pytest.mark.parametrize("kind,widths", [("zinc", (21, 4)), ("counting", None)])
+def test_fused_collation_into_padded_buffers_is_bit_exact(kind, widths):
+    """gnnml3_collate writing straight into the static (padded) buffers of a captured step -- from the wire format and from the
+    HBM-resident pool -- equals train.pad_batch of the host-collated batch, field by field (integer work; floats are copied)."""
+    from gnn_matlang_b200.batch import Batch, CompactBatch
+    from gnn_matlang_b200.synthetic import DeviceDataset, GraphPool
+    from gnn_matlang_b200.train import pad_batch
+    pool = GraphPool(kind, 64, seed=9)
+    idx = np.random.default_rng(5).integers(0, 64, 1500)          # more than 1024 graphs: two chunks of the offset scan
+    hb = pool.collate(idx)
+    N, E = hb.x.size(0), hb.edge_index2.size(1)
+    Np, Ep = N + 37, E + 211
+    ref = pad_batch(hb, Np, Ep)
+    d = dev()
+
+    def static():
+        return Batch(x=torch.full((Np, hb.x.size(1)), 7.0, device=d), edge_index2=torch.full((2, Ep), -1, dtype=torch.int64, device=d),
+                     edge_attr2=torch.full((Ep, hb.edge_attr2.size(1)), 7.0, device=d), batch=torch.full((Np,), -1, dtype=torch.int64, device=d),
+                     graph_ptr=torch.full((len(idx) + 2,), -1, dtype=torch.int32, device=d), y=torch.zeros_like(hb.y, device=d),
+                     num_graphs=len(idx) + 1)
+
+    a = CompactBatch.from_batch(hb, widths).pin_memory().to(d).expand_into(static())
+    b = DeviceDataset(pool, d).collate_into(torch.from_numpy(idx).pin_memory(), static())
+    for out in (a, b):
+        for k in FIELDS:
+            assert torch.equal(getattr(out, k).cpu(), getattr(ref, k)), k
