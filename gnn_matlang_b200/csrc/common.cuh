@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <mutex>
+
 #include "../../include/gnnml3_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -43,14 +45,27 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 // cudaFuncSetAttribute is per device: `flags` is a per-kernel static array, true once the attribute was set on the current
-// device (a process normally drives one GPU, but nothing here assumes it).  Benign race: the attribute call is idempotent.
-static inline bool first_use_on_device(bool (&flags)[64]) {
+// device (a process normally drives one GPU, but nothing here assumes it).  Thread-safe (the autograd engine calls backward
+// from its own thread): the first caller on a device gets a guard that holds the library's configuration mutex until the
+// attribute calls in the `if` body are done, and only then publishes the flag; later callers take the lock-free path.
+//     if (auto once = first_use_on_device(configured)) GNNML3_CUDA(cudaFuncSetAttribute(...));
+std::mutex& config_mutex();      // runtime.cu
+struct DeviceOnce {
+    bool* flag;
+    std::unique_lock<std::mutex> lock;
+    explicit operator bool() const { return flag != nullptr; }
+    ~DeviceOnce() {
+        if (flag) __atomic_store_n(flag, true, __ATOMIC_RELEASE);
+    }
+};
+static inline DeviceOnce first_use_on_device(bool (&flags)[64]) {
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (flags[dev]) return false;
-    flags[dev] = true;
-    return true;
+    if (__atomic_load_n(&flags[dev], __ATOMIC_ACQUIRE)) return DeviceOnce{nullptr, {}};
+    std::unique_lock<std::mutex> lk(config_mutex());
+    if (flags[dev]) return DeviceOnce{nullptr, {}};
+    return DeviceOnce{&flags[dev], std::move(lk)};
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -12,6 +12,8 @@
 
 #include <stdlib.h>
 
+#include <atomic>
+
 namespace gnnml3 {
 
 template <int K>
@@ -268,7 +270,7 @@ static int g_edge_tc = [] {
     const char* e = getenv("GNNML3_EDGE_TC");
     return (e && e[0] == '0') ? 0 : 1;
 }();
-static long long g_edge_paths[2] = {0, 0};   // launches of [tensor-core, CUDA-core] edge-MLP kernels (forward + backward)
+static std::atomic<long long> g_edge_paths[2];   // launches of [tensor-core, CUDA-core] edge-MLP kernels (forward + backward)
 
 extern "C" int gnnml3_edge_mlp_set_tc(int enable) {
     const int old = g_edge_tc;
@@ -276,9 +278,8 @@ extern "C" int gnnml3_edge_mlp_set_tc(int enable) {
     return old;
 }
 extern "C" int gnnml3_edge_mlp_path_counts(long long* out2_host, int reset) {
-    out2_host[0] = g_edge_paths[0];
-    out2_host[1] = g_edge_paths[1];
-    if (reset) g_edge_paths[0] = g_edge_paths[1] = 0;
+    out2_host[0] = reset ? g_edge_paths[0].exchange(0) : g_edge_paths[0].load();
+    out2_host[1] = reset ? g_edge_paths[1].exchange(0) : g_edge_paths[1].load();
     return GNNML3_OK;
 }
 
@@ -330,7 +331,7 @@ static int launch_edge_bwd(const float* ea, const int32_t* eperm, const float* g
                            float* dw4, float* partial, cudaStream_t st) {
     using C = EMC<K>;
     static bool configured[64] = {};
-    if (first_use_on_device(configured)) {
+    if (auto once_ = first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_edge_mlp_bwd<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem));
         GNNML3_CUDA(cudaFuncSetAttribute(k_edge_mlp_bwd<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bwd_smem));
     }

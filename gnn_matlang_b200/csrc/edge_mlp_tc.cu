@@ -564,7 +564,7 @@ template <int K, int MODE>
 static int emt_launch(const EMTParams& p, int* nparts, cudaStream_t st) {
     using T = EMT<K>;
     static bool configured[64] = {};
-    if (first_use_on_device(configured))
+    if (auto once_ = first_use_on_device(configured))
         GNNML3_CUDA(cudaFuncSetAttribute(k_edge_mlp_tc<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::smem_bytes(MODE)));
     constexpr int NWG = T::nwg(MODE);
     const int64_t ntiles = (p.E + 127) / 128;

@@ -914,7 +914,7 @@ extern "C" int gnnml3_fused_profile_fetch(double* out, int max) {
 template <int KT, int BNH, int NAGG, bool RES>
 static int fl_launch2(const CUtensorMap& mW, FLParams& P, size_t smem, cudaStream_t st) {
     static bool configured[64] = {};
-    if (first_use_on_device(configured))
+    if (auto once_ = first_use_on_device(configured))
         GNNML3_CUDA(cudaFuncSetAttribute(k_fused_agg_proj<KT, BNH, NAGG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FL_SMEM_MAX));
     const int grid = P.n_tiles < kNumSMs ? P.n_tiles : kNumSMs;

@@ -26,6 +26,7 @@
 #include "tc_common.cuh"
 
 #include <cuda_bf16.h>
+#include <atomic>
 #include <vector>
 
 namespace gnnml3 {
@@ -935,11 +936,10 @@ static int g_ts_runtime_enabled = 1;
 
 // which kernel gnnml3_fused_agg_proj dispatched to since the last reset: [0] tensor-memory kernel, [1] round-1 shared-memory
 // plane kernel; the Python side adds the counts of the two-kernel fallback (bench.py prints them as `path_taken`)
-static long long g_fused_paths[2] = {0, 0};
+static std::atomic<long long> g_fused_paths[2];
 extern "C" int gnnml3_fused_path_counts(long long* out2_host, int reset) {
-    out2_host[0] = g_fused_paths[0];
-    out2_host[1] = g_fused_paths[1];
-    if (reset) g_fused_paths[0] = g_fused_paths[1] = 0;
+    out2_host[0] = reset ? g_fused_paths[0].exchange(0) : g_fused_paths[0].load();
+    out2_host[1] = reset ? g_fused_paths[1].exchange(0) : g_fused_paths[1].load();
     return GNNML3_OK;
 }
 namespace gnnml3 {
@@ -1000,7 +1000,7 @@ TSProfHook g_ts_prof = {nullptr, nullptr};
 template <int KT, int BNH>
 static int ts_launch(const CUtensorMap& mW, const CUtensorMap& mX, TSParams& P, size_t smem, cudaStream_t st) {
     static bool configured[64] = {};
-    if (first_use_on_device(configured))
+    if (auto once_ = first_use_on_device(configured))
         GNNML3_CUDA(cudaFuncSetAttribute(k_fused_ts<KT, BNH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM_MAX));
     const int grid = P.n_tiles < kNumSMs ? P.n_tiles : kNumSMs;
     k_fused_ts<KT, BNH><<<grid, TS_THREADS, smem, st>>>(mW, mX, P);

@@ -373,7 +373,7 @@ extern "C" size_t gnnml3_fused_sddmm_workspace_bytes(int K) { return align_up((s
 template <int K>
 static int sd_launch(const CUtensorMap& mW, const CUtensorMap& mX, SDParams& P, cudaStream_t st) {
     static bool configured[64] = {};
-    if (first_use_on_device(configured)) {
+    if (auto once_ = first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_fused_sddmm<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM));
     }
     const int grid = P.n_tiles < kNumSMs ? P.n_tiles : kNumSMs;

@@ -483,7 +483,7 @@ template <int BN, bool VA, bool VB, bool X3>
 static int launch_nn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                      int64_t M, int Nc, int Kc, int epi, cudaStream_t st) {
     static bool configured[64] = {};
-    if (first_use_on_device(configured)) {
+    if (auto once_ = first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_nn<BN, VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)nn_smem_bytes<BN>()));
     }
@@ -536,7 +536,7 @@ template <int BA, int BB, bool VA, bool VB, bool X3>
 static int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb,
                      int splits, int64_t rps, cudaStream_t st) {
     static bool configured[64] = {};
-    if (first_use_on_device(configured)) {
+    if (auto once_ = first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn<BA, BB, VA, VB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn_smem_bytes<BA, BB>()));
     }
     dim3 grid(cdiv(Ka, BA), cdiv(Nb, BB), splits);

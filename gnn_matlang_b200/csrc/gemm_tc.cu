@@ -257,7 +257,7 @@ static int launch_tc(const float* A, int64_t lda, const float* hi, const float* 
                      float* C, int64_t ldc, int64_t M, int Nc, int Kc, int epi, int chunk_kb, cudaStream_t st) {
     using Cfg = TCCfg<BN>;
     static bool configured[64] = {};
-    if (first_use_on_device(configured)) {
+    if (auto once_ = first_use_on_device(configured)) {
         GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_nn_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     }
     CUtensorMap mapA, mapBhi, mapBlo;

@@ -213,7 +213,7 @@ static int tt_make_map(CUtensorMap* map, const float* base, int64_t rows, int64_
 int gemm_tn_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb,
                       cudaStream_t st) {
     static bool configured[64] = {};
-    if (first_use_on_device(configured))
+    if (auto once_ = first_use_on_device(configured))
         GNNML3_CUDA(cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT_SMEM));
     CUtensorMap mapA, mapB;
     int rc;

@@ -20,6 +20,11 @@ int set_err(int code, const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+std::mutex& config_mutex() {
+    static std::mutex m;
+    return m;
+}
+
 }  // namespace gnnml3
 
 extern "C" {

@@ -351,13 +351,16 @@ extern "C" int gnnml3_spectral_design(const int64_t* edge_index, int64_t Etot, c
     P.recfield = recfield; P.nfreq = nfreq; P.laplacien = laplacien; P.addadj = addadj; P.has_vmax = has_vmax;
     P.global_ids = global_ids; P.dv = dv; P.vmax = vmax;
     const size_t smem = sd_smem_bytes(nmax, nfreq);
-    static size_t configured[64] = {};
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    dev_ &= 63;
-    if (smem > configured[dev_]) {
-        GNNML3_CUDA(cudaFuncSetAttribute(k_sd_design, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev_] = smem;
+    {   // the attribute grows with the largest graph seen on this device; guarded like every other per-device configuration
+        static size_t configured[64] = {};
+        int dev_ = 0;
+        cudaGetDevice(&dev_);
+        dev_ &= 63;
+        std::lock_guard<std::mutex> lk(config_mutex());
+        if (smem > configured[dev_]) {
+            GNNML3_CUDA(cudaFuncSetAttribute(k_sd_design, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev_] = smem;
+        }
     }
     k_sd_design<<<B, SD_THREADS, smem, (cudaStream_t)stream_>>>(edge_index, Etot, edge_ptr, node_ptr, P, nmax, out_ptr,
                                                                  edge_index2, E2, edge_attr2, lmax, degree);

@@ -43,6 +43,12 @@ def pytest_terminal_summary(terminalreporter):
         st = test_gpu_kernels.PURE_RTOL_STATS
     except Exception:
         return
+    try:
+        import test_gpu_model
+        for line in test_gpu_model.SEED_LOG:
+            terminalreporter.write_line("whole-model gradient parity -- " + line)
+    except Exception:
+        pass
     if st["entries"]:
         terminalreporter.write_line("assert_close: %d calls, %d entries compared, %.4f %% within the plain element-wise rtol"
                                     % (st["calls"], st["entries"], 100.0 * st["within_pure_rtol"] / st["entries"]))

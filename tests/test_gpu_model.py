@@ -163,6 +163,9 @@ def _random_graphs(cfg, nb, g):
     return out
 
 
+SEED_LOG = []       # which seeded batch each whole-model gradient check passed on (printed by conftest.pytest_terminal_summary)
+
+
 def _kink_margin(ref, ob):
     """Smallest |pre-activation| / max|pre-activation| over every ReLU of the oracle model (edge MLP, conv, head).
     ReLU makes the gradient discontinuous: a pre-activation within rounding distance of 0 gets a different mask
@@ -239,6 +242,8 @@ def test_model_training_step_matches_oracle(cfg):
     for seed in range(4):
         ok, (node_m, edge_m), msg = _train_step_compare(cfg, seed)
         if ok:
+            SEED_LOG.append("%s: seed %d passed (node margin %.1e, edge margin %.1e)%s"
+                            % (cfg, seed, node_m, edge_m, "; excused before: " + " | ".join(msgs) if msgs else ""))
             return
         msgs.append("seed %d: node margin %.1e edge margin %.1e: %s" % (seed, node_m, edge_m, msg[:200]))
         assert node_m < 1e-5 or edge_m < 1e-6, "gradient mismatch without a ReLU kink nearby: " + msgs[-1]
