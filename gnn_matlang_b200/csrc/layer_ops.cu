@@ -112,10 +112,22 @@ k_ml3_act_bwd_y(const float* __restrict__ y, int64_t ldy, const float* __restric
         const int rl = i / ngroups, cg = i - rl * ngroups, c = 4 * cg;
         const int64_t n = r0 + rl;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (c + 3 < Fo && vec_in) {
+        if (c < Fo && vec_in && c + 3 < (int)ldy && c + 3 < (int)ldgy) {
+            // (the group that straddles Fo reads the whole 16-byte chunk too -- it lies inside the row -- and masks the tail:
+            // its scalar path made every warp execute both branches)
             const float4 yy = ldg4(y + n * ldy + c), gg = ldg4(gy + n * ldgy + c);
-            v[0] = yy.x > 0.f ? gg.x : 0.f; v[1] = yy.y > 0.f ? gg.y : 0.f;
-            v[2] = yy.z > 0.f ? gg.z : 0.f; v[3] = yy.w > 0.f ? gg.w : 0.f;
+            v[0] = yy.x > 0.f ? gg.x : 0.f;
+            v[1] = (c + 1 < Fo && yy.y > 0.f) ? gg.y : 0.f;
+            v[2] = (c + 2 < Fo && yy.z > 0.f) ? gg.z : 0.f;
+            v[3] = (c + 3 < Fo && yy.w > 0.f) ? gg.w : 0.f;
+        } else if (c >= Fo4 && G == 2 && c == Fo4 && vec_in && ldaux % 4 == 0 && ((uintptr_t)aux & 15) == 0 && Fo + 1 < (int)ldgy) {
+            // the common gate block (G = 2): [g1_0 g1_1 g2_0 g2_1] from one 16-byte load of the saved tanh factors
+            const float4 t = ldg4(aux + n * ldaux);                    // t1_0 t1_1 t2_0 t2_1
+            const float g0 = __ldg(gy + n * ldgy + Fo), g1 = __ldg(gy + n * ldgy + Fo + 1);
+            v[0] = g0 * t.z * (1.f - t.x * t.x);
+            v[1] = g1 * t.w * (1.f - t.y * t.y);
+            v[2] = g0 * t.x * (1.f - t.z * t.z);
+            v[3] = g1 * t.y * (1.f - t.w * t.w);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

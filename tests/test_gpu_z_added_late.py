@@ -112,3 +112,54 @@ def test_ml3layer_without_learned_edges_ignores_extra_channels():
     a = layer(x, ei, ea)
     b = layer(x, ei, ea[:, :K].contiguous())
     assert torch.equal(a, b)
+
+
+def _dot(a, b):
+    return float((a.double() * b.double()).sum())
+
+
+@pytest.mark.parametrize("case", ["zinc_step_fused", "sweep_1M_nodes_f64"])
+def test_full_size_adjoint_and_linearity_properties(case):
+    """Parity at BASELINE.json's full sizes, where the CPU oracle would take minutes: size-independent properties of SpectConv.
+    The layer (without bias) is bilinear in (x, edge_attr), so for random g
+        <conv(x, ea), g> = <x, dL/dx> = <ea, dL/dea>            (L = <conv, g>: adjointness of the forward kernel and the two
+                                                                 backward kernels -- fused dx over the transposed CSR, fused /
+                                                                 two-kernel SDDMM)
+        conv(a x1 + b x2, ea) = a conv(x1, ea) + b conv(x2, ea) (linearity)
+        <W_k, dL/dW_k> summed over k = <conv, g>                (weight gradient, Euler's identity for a linear map)
+    must hold to FP32 accuracy.  zinc_step_fused: the 8192-graph ZINC batch (K = 8, 32 -> 30: tensor-memory fused kernels);
+    sweep_1M_nodes_f64: BASELINE configs[4] (1 M nodes, K = 10, F = 64: shared-memory plane kernel + two-kernel backward)."""
+    from gnn_matlang_b200.libs.spect_conv import SpectConv
+    from gnn_matlang_b200.synthetic import GraphPool
+    d = torch.device("cuda:0")
+    rng = np.random.default_rng(7)
+    if case == "zinc_step_fused":
+        pool = GraphPool("zinc", 512, seed=2)
+        hb = pool.draw(rng, 8192)
+        K, Fi, Fo = pool.K, 32, 30
+    else:
+        pool = GraphPool("sweep", 256, seed=1, K=10, nfeat=4, recfield=1)
+        hb = pool.draw(rng, int(1000000 / float(pool.n.mean())))
+        K, Fi, Fo = 10, 64, 64
+    N = hb.x.shape[0]
+    ei = hb.edge_index2.to(d)
+    torch.manual_seed(1)
+    layer = SpectConv(Fi, Fo, K, selfconn=False, bias=False).to(d)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    ea = (torch.randn(ei.size(1), K, generator=g) * 0.3).to(d).requires_grad_(True)
+    x1 = torch.randn(N, Fi, generator=g).to(d).requires_grad_(True)
+    x2 = torch.randn(N, Fi, generator=g).to(d)
+    gout = torch.randn(N, Fo, generator=g).to(d)
+    y1 = layer(x1, ei, ea)
+    y1.backward(gout)
+    L = _dot(y1.detach(), gout)
+    scale = float((y1.double().abs() * gout.double().abs()).sum())         # sum of |terms|: the rounding scale of the dot product
+    assert abs(_dot(x1.detach(), x1.grad) - L) <= 2e-6 * scale, ("dx", _dot(x1.detach(), x1.grad), L, scale)
+    assert abs(_dot(ea.detach(), ea.grad) - L) <= 2e-6 * scale, ("dea", _dot(ea.detach(), ea.grad), L, scale)
+    assert abs(_dot(layer.weight.detach(), layer.weight.grad) - L) <= 2e-6 * scale, ("dW", _dot(layer.weight.detach(), layer.weight.grad), L)
+    with torch.no_grad():
+        y2 = layer(x2, ei, ea.detach())
+        y3 = layer(0.75 * x1.detach() - 1.5 * x2, ei, ea.detach())
+    ref = 0.75 * y1.detach().double() - 1.5 * y2.double()
+    err = (y3.double() - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
