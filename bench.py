@@ -378,6 +378,79 @@ def exp_config(dev, B, steps, warmup, cpu_sample=True):
     return out
 
 
+def graph8c_config(dev, cpu_seconds=3.0):
+    """BASELINE.json configs[0]: graph8c.py:281-302 -- embed all 11,117 8-node graphs with a fresh seed-0 GNNML3 in batches of 100
+    and count the pairs whose embeddings differ by less than 1e-3 in L1 (known answer after seed 0: 1 pair).  Everything on the
+    GPU through the product path: graph6 reader -> SpectralDesign (one launch for the whole dataset) -> HBM-resident dataset ->
+    on-device collation -> forward.  The CPU figure beside it is the oracle port on a bounded sample of the same batches."""
+    from gnn_matlang_b200.datasets import read_graph6
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    from gnn_matlang_b200.models import GNNML3
+    from gnn_matlang_b200.synthetic import DeviceDataset
+    path = os.path.join(ROOT, "tests", "golden", "graph8c.g6")
+    recs = read_graph6(path)
+    ns = np.array([r["x"].shape[0] for r in recs], np.int64)
+    es = np.array([r["edge_index"].shape[1] for r in recs], np.int64)
+    node_ptr, edge_ptr = np.concatenate([[0], np.cumsum(ns)]), np.concatenate([[0], np.cumsum(es)])
+    ei = torch.from_numpy(np.concatenate([r["edge_index"] for r in recs], 1))
+    sd = SpectralDesign(recfield=1, dv=2, nfreq=5, adddegree=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ei_d, ep_d, np_d = ei.to(dev), torch.from_numpy(edge_ptr).to(dev), torch.from_numpy(node_ptr)
+    design = sd.design_batch(ei_d, ep_d, np_d, device=dev)              # warm-up (also sizes the outputs)
+    torch.cuda.synchronize()
+    e0.record()
+    design = sd.design_batch(ei_d, ep_d, np_d, device=dev)
+    e1.record()
+    torch.cuda.synchronize()
+    sd_ms = e0.elapsed_time(e1)
+    x = torch.cat([torch.ones(int(node_ptr[-1]), 1, device=dev), design["degree"].unsqueeze(-1)], 1)
+    dds = DeviceDataset.from_design(design, node_ptr, x)
+    torch.manual_seed(0)
+    model = GNNML3("graph8c", ne=6, ninp=2).to(dev).eval()
+    G = len(recs)
+    idx = [torch.arange(s, min(s + 100, G)).pin_memory() for s in range(0, G, 100)]
+
+    def embed_all():
+        out = []
+        with torch.no_grad():
+            for ix in idx:
+                out.append(model(dds.collate(ix)))
+        return torch.cat(out)
+
+    embed_all()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    emb = embed_all()
+    e1.record()
+    torch.cuda.synchronize()
+    ms, wall = e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3
+    similar = 0
+    for r in range(0, G, 2048):
+        similar += int((torch.cdist(emb[r:r + 2048], emb, p=1) <= 0.001).sum())
+    similar = (similar - G) // 2
+    out = {"reference_script": "graph8c.py:281-302 GNNML3 (3 x ML3Layer 32||16, K=6, add-pool, tanh head) isomorphism test, 11,117 graphs, batches of 100, seed 0",
+           "graphs": G, "batches": len(idx), "ms_embed_all": ms, "wall_ms_embed_all": wall, "graphs_per_s": G / (ms * 1e-3),
+           "undistinguished_pairs_after_seed_0": similar, "known_answer": 1,
+           "spectral_design": {"gpu_ms_all_graphs": sd_ms, "gpu_graphs_per_s": G / (sd_ms * 1e-3)},
+           "note": "forward only, launch by launch (112 small batches: host-enqueue bound, wall = device time)"}
+    if cpu_seconds > 0:
+        from oracle import gnnml3_oracle as O
+        g8 = O.parse_graph6(path)
+        torch.manual_seed(0)
+        ref = O.OracleGNNML3("graph8c", 6, 2)
+        kw = dict(recfield=1, dv=2, nfreq=5, adddegree=True)
+        done, t0 = 0, time.perf_counter()
+        with torch.no_grad():
+            while time.perf_counter() - t0 < cpu_seconds and done < G:
+                graphs = [O.spectral_design(e, np.ones((n, 1), np.float32), **kw) for n, e in g8[done:done + 100]]
+                ref(O.collate(graphs))
+                done += len(graphs)
+        out["cpu_baseline"] = {"kind": "port", "cores": os.cpu_count(), "value": done / (time.perf_counter() - t0), "unit": "graphs/s",
+                               "sample": "%d graphs: oracle SpectralDesign (numpy eigh per graph) + oracle forward in batches of 100" % done}
+    return out
+
+
 def ncu_shares():
     """Per-kernel shares of ONE step of the timed code path, from the committed `ncu --metrics gpu__time_duration.sum` launch
     list of the same command (cold-cache, serialised: shares, not absolutes)."""
@@ -684,17 +757,20 @@ def main():
     other = None
     if rank == 0 and world == 1 and not args.no_other_configs and args.workload == "zinc":
         other = {}
-        try:
-            other["zinc_reference_batch_64"] = small_config(dev, "zinc", 64, 100, 20)
-            other["counting_batch_128"] = small_config(dev, "counting", 128, 100, 20)
-            other["exp_spectral_design_on_gpu"] = exp_config(dev, 4096, 10, 3)
-            other["exp_reference_batch_50"] = exp_config(dev, 50, 50, 10, cpu_sample=False)
-            sweep = []
-            for F, hops, st in ((64, 1, 5), (64, 2, 3), (128, 1, 3), (256, 1, 2)):
-                sweep.append(sweep_one(dev, F, 10, 1000000, hops, st, 2))
-            other["spectconv_sweep_1M_nodes"] = sweep
-        except Exception as ex:          # a failure here must not take the headline line down with it; it is reported
-            other["error"] = "%s: %s" % (type(ex).__name__, ex)
+
+        def attempt(name, fn):           # a failure here must not take the headline line (or the other entries) down; it is reported
+            try:
+                other[name] = fn()
+            except Exception as ex:
+                other[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
+        attempt("graph8c_isomorphism_eval", lambda: graph8c_config(dev, 0.0 if args.no_cpu_baseline else 3.0))
+        attempt("zinc_reference_batch_64", lambda: small_config(dev, "zinc", 64, 100, 20))
+        attempt("counting_batch_128", lambda: small_config(dev, "counting", 128, 100, 20))
+        attempt("exp_spectral_design_on_gpu", lambda: exp_config(dev, 4096, 10, 3))
+        attempt("exp_reference_batch_50", lambda: exp_config(dev, 50, 50, 10, cpu_sample=False))
+        attempt("spectconv_sweep_1M_nodes", lambda: [sweep_one(dev, F, 10, 1000000, hops, st, 2)
+                                                     for F, hops, st in ((64, 1, 5), (64, 2, 3), (128, 1, 3), (256, 1, 2))])
 
     if rank == 0:
         edge_attr = pool.supports if not is_exp else ExpPool.supports

@@ -266,6 +266,27 @@ class DeviceDataset(object):
         self.ea = t(pool.ea2)
         self.y = t(pool.y)
 
+    @classmethod
+    def from_design(cls, design, node_ptr, x, y=None):
+        """Resident dataset straight from ``SpectralDesign.design_batch(global_ids=False)`` (everything stays on the device):
+        ``design['edge_index2']`` holds graph-local ids, ``design['e2_ptr']`` / ``node_ptr`` are the record offsets, ``x [Ntot, F]``
+        the node features (degree column already appended when the design asks for it)."""
+        self = cls.__new__(cls)
+        dev = design["edge_attr2"].device
+        self.device = dev
+        npd = torch.as_tensor(node_ptr).to(dev, torch.int64)
+        e2 = design["e2_ptr"].to(dev, torch.int64)
+        self.n, self.e = npd[1:] - npd[:-1], e2[1:] - e2[:-1]
+        self.n32, self.e32 = self.n.to(torch.int32), self.e.to(torch.int32)
+        self.n_h, self.e_h = self.n.cpu().numpy(), self.e.cpu().numpy()
+        self.node_off, self.edge_off = npd.contiguous(), e2.contiguous()
+        self.x = x.to(dev, torch.float32).contiguous()
+        self.el = design["edge_index2"].contiguous()
+        self.ea = design["edge_attr2"].contiguous()
+        B = self.n.numel()
+        self.y = (torch.zeros(B, device=dev) if y is None else torch.as_tensor(y).to(dev)).reshape(B, -1)
+        return self
+
     def _idx(self, idx_host):
         idx_np = idx_host.numpy() if isinstance(idx_host, torch.Tensor) else np.asarray(idx_host)
         idx = (idx_host if isinstance(idx_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(idx_np))).to(

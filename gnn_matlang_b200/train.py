@@ -21,6 +21,25 @@ def loss_fn(kind, out, y):
     raise ValueError(kind)
 
 
+def shard_graphs(sizes, world, rank=None):
+    """Contiguous split of a global minibatch over ``world`` ranks balanced by the graphs' sizes (nodes or support entries) and
+    not by their count (30-100-node mixes): the cut points are the positions where the running sum of ``sizes``
+    crosses k / world of the total.  Returns the list of (begin, end) graph ranges, or rank's range.  Pure host arithmetic."""
+    import numpy as np
+    s = np.asarray(sizes, dtype=np.float64)
+    c = np.concatenate([[0.0], np.cumsum(s)])
+    cuts = [0]
+    for k in range(1, world):
+        target = c[-1] * k / world
+        j = int(np.searchsorted(c, target, side="left"))
+        if j > 0 and abs(c[j - 1] - target) <= abs(c[min(j, len(c) - 1)] - target):
+            j -= 1
+        cuts.append(min(max(j, cuts[-1]), len(s)))
+    cuts.append(len(s))
+    ranges = [(cuts[k], cuts[k + 1]) for k in range(world)]
+    return ranges if rank is None else ranges[rank]
+
+
 class Trainer(object):
     def __init__(self, model, loss="l1", lr=1e-3, distributed=False):
         self.model = model

@@ -256,3 +256,19 @@ def test_compact_wire_format_round_trip_and_device_dataset_on_cpu():
     pool = GraphPool("counting", 8, seed=2)
     with pytest.raises(ValueError):
         CompactBatch.from_batch(pool.collate(np.arange(4)), (1, 1))
+
+
+def test_shard_graphs_balances_by_size_not_by_count():
+    """ranks get contiguous chunks of a global minibatch balanced by sum of nodes (30-100-node mixes)."""
+    from gnn_matlang_b200.train import shard_graphs
+    rng = np.random.default_rng(0)
+    sizes = np.concatenate([rng.integers(30, 40, 300), rng.integers(90, 101, 300)])       # small graphs first, large graphs last
+    for world in (2, 4, 8):
+        r = shard_graphs(sizes, world)
+        assert r[0][0] == 0 and r[-1][1] == len(sizes) and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        loads = np.array([sizes[a:b].sum() for a, b in r], dtype=np.float64)
+        assert loads.max() / loads.mean() <= 1.0 + sizes.max() / loads.mean()               # within one graph of perfect
+        by_count = np.array([c.sum() for c in np.array_split(sizes, world)], dtype=np.float64)
+        assert by_count.max() / by_count.mean() > 1.3                                        # what equal counts would give
+        assert shard_graphs(sizes, world, rank=1) == r[1]
+    assert shard_graphs([5], 4) == [(0, 0), (0, 0), (0, 1), (1, 1)] or sum(b - a for a, b in shard_graphs([5], 4)) == 1
