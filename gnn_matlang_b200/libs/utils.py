@@ -39,7 +39,8 @@ class SpectralDesign(object):
         return self.nfreq + 1 + (1 if self.addadj else 0)
 
     # ------------------------------------------------------------------------------------------ batched
-    def design_batch(self, edge_index, edge_ptr, node_ptr, device=None, global_ids=False, max_entries=None):
+    def design_batch(self, edge_index, edge_ptr, node_ptr, device=None, global_ids=False, max_entries=None, nmax=None,
+                     num_nodes=None):
         """edge_index [2, Etot] int64 with LOCAL node ids, edge_ptr / node_ptr [B+1] (any int dtype, any device).
         Returns a dict of device tensors: edge_index2 [2, E2], edge_attr2 [E2, K], e2_ptr [B+1] (int64),
         lmax [B], degree [Ntot].
@@ -48,19 +49,32 @@ class SpectralDesign(object):
         synchronisation per call).  With ``max_entries`` (an upper bound, e.g. ``sum(n_b ** 2)``) nothing is read back:
         the outputs have ``max_entries`` columns / rows, the tail beyond ``e2_ptr[-1]`` holds entries (0, 0) with all-zero
         supports -- exactly neutral for SpectConv / ML3Layer (they add 0 to node 0 and receive zero gradients) -- so the
-        call is CUDA-graph capturable and the downstream CSR build needs no size from the device."""
+        call is CUDA-graph capturable and the downstream CSR build needs no size from the device.
+
+        ``node_ptr`` may be a DEVICE tensor when the caller also passes ``nmax`` (largest graph) and ``num_nodes`` (total):
+        nothing is uploaded then (uploading a pageable host tensor synchronises the stream: with designs of several batches in
+        flight on different streams that upload was the serialisation point -- train.DesignFeeder)."""
         lib = _lib.load()
         if device is None:
             device = edge_index.device if edge_index.is_cuda else torch.device("cuda", torch.cuda.current_device())
         if not torch.cuda.is_available():
             raise RuntimeError("gnn_matlang_b200.SpectralDesign needs a CUDA device (no CPU fallback)")
-        node_ptr_h = torch.as_tensor(node_ptr).to("cpu", torch.int64)
-        B = node_ptr_h.numel() - 1
-        nmax = int((node_ptr_h[1:] - node_ptr_h[:-1]).max()) if B > 0 else 1
+        if isinstance(node_ptr, torch.Tensor) and node_ptr.is_cuda:
+            if nmax is None or num_nodes is None:
+                raise ValueError("design_batch: a device node_ptr needs nmax= and num_nodes=")
+            B = node_ptr.numel() - 1
+            npd = node_ptr.to(dtype=torch.int32).contiguous()
+            Ntot_given = int(num_nodes)
+            nmax = int(nmax)
+        else:
+            node_ptr_h = torch.as_tensor(node_ptr).to("cpu", torch.int64)
+            B = node_ptr_h.numel() - 1
+            nmax = int((node_ptr_h[1:] - node_ptr_h[:-1]).max()) if B > 0 else 1
+            npd = node_ptr_h.to(device=device, dtype=torch.int32).contiguous()
+            Ntot_given = int(node_ptr_h[-1]) if B > 0 else 0
         ei = torch.as_tensor(edge_index).to(device=device, dtype=torch.int64).contiguous()
         ep = torch.as_tensor(edge_ptr).to(device=device, dtype=torch.int32).contiguous()
-        npd = node_ptr_h.to(device=device, dtype=torch.int32).contiguous()
-        Etot, Ntot = ei.size(1), int(node_ptr_h[-1]) if B > 0 else 0
+        Etot, Ntot = ei.size(1), Ntot_given
         K = self.num_supports
         counts = torch.zeros(B, dtype=torch.int32, device=device)
         with torch.cuda.device(device):
@@ -84,7 +98,7 @@ class SpectralDesign(object):
                 int(bool(self.laplacien)), int(bool(self.addadj)), int(self.vmax is not None),
                 float(self.vmax if self.vmax is not None else 0.0), max(nmax, 1), _lib.ptr(e2_ptr), int(bool(global_ids)),
                 _lib.ptr(ei2), E2, _lib.ptr(ea2), _lib.ptr(lmax), _lib.ptr(deg), st), "gnnml3_spectral_design")
-        return dict(edge_index2=ei2, edge_attr2=ea2, e2_ptr=e2_ptr, lmax=lmax, degree=deg)
+        return dict(edge_index2=ei2, edge_attr2=ea2, e2_ptr=e2_ptr, counts=counts, lmax=lmax, degree=deg)
 
     def design_list(self, graphs, device=None):
         """``graphs``: list of (n, edge_index [2,e]) pairs -> per-graph list of dicts (edge_index2, edge_attr2,

@@ -225,6 +225,7 @@ class ExpPool(object):
         esel = np.repeat(self.edge_off1[idx] - eoff[:-1], e) + np.arange(eoff[-1])
         return dict(x=torch.from_numpy(self.x[nsel]), edge_index=torch.from_numpy(self.ei1[:, esel]),
                     edge_ptr=torch.from_numpy(eoff.astype(np.int32)), node_ptr=torch.from_numpy(goff.astype(np.int32)),
+                    node_ptr_dev=torch.from_numpy(goff.astype(np.int32)), nmax=int(n.max()) if B > 0 else 1,
                     y=torch.from_numpy(self.y[idx]).reshape(-1, 1), num_graphs=int(B))
 
 
@@ -234,17 +235,36 @@ def design_and_collate(raw, sd, device):
     (PyG's collation of ``edge_index2`` is the per-graph node offset the kernel adds), ``x`` gets the degree column
     (``adddegree``) and ``batch`` / ``graph_ptr`` come from ``node_ptr``."""
     node_ptr = raw["node_ptr"]
-    out = sd.design_batch(raw["edge_index"], raw["edge_ptr"], node_ptr, device=device, global_ids=True)
+    npd = raw.get("node_ptr_dev")                  # device copy made when the batch was drawn: nothing is uploaded per step
+    if npd is not None and npd.is_cuda:
+        out = sd.design_batch(raw["edge_index"], raw["edge_ptr"], npd, device=device, global_ids=True, nmax=raw["nmax"],
+                              num_nodes=int(node_ptr[-1]))
+        gp = npd.to(torch.int32)
+    else:
+        out = sd.design_batch(raw["edge_index"], raw["edge_ptr"], node_ptr, device=device, global_ids=True)
+        gp = node_ptr.to(device=device, dtype=torch.int32)
     x = raw["x"].to(device, non_blocking=True)
     if sd.adddegree:
         x = torch.cat([x, out["degree"].unsqueeze(-1)], 1)
-    gp = node_ptr.to(device=device, dtype=torch.int32)
     B = node_ptr.numel() - 1
     batch = torch.repeat_interleave(torch.arange(B, device=device), (gp[1:] - gp[:-1]).long(), output_size=int(x.size(0)))
     b = Batch(x=x, edge_index2=out["edge_index2"], edge_attr2=out["edge_attr2"], batch=batch, num_graphs=B, graph_ptr=gp,
               y=raw["y"].to(device, non_blocking=True))
     b.batch._gnnml3_ptr = (b.batch._version, gp)
     return b
+
+
+def design_raw(raw, sd, device):
+    """Raw graphs with device-resident fields (``ExpPool.draw_raw`` moved to the device, incl. ``node_ptr_dev`` / ``nmax``) -> the
+    per-graph records ``gnnml3_collate`` batches: supports with graph-LOCAL ids, entry counts, features with the degree column.
+    No upload, one read-back (the entry total that sizes the outputs)."""
+    npd = raw["node_ptr_dev"]
+    out = sd.design_batch(raw["edge_index"], raw["edge_ptr"], npd, device=device, global_ids=False, nmax=raw["nmax"],
+                          num_nodes=int(raw["node_ptr"][-1]))
+    x = raw["x"]
+    if sd.adddegree:
+        x = torch.cat([x, out["degree"].unsqueeze(-1)], 1)
+    return dict(design=out, x=x.contiguous(), n32=(npd[1:] - npd[:-1]).to(torch.int32), num_graphs=int(npd.numel() - 1), y=raw["y"])
 
 
 class DeviceDataset(object):

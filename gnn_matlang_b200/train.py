@@ -127,6 +127,46 @@ class HostFeeder(object):
         return self.get_compact().expand()
 
 
+class DesignFeeder(object):
+    """BASELINE.json configs[2] (exp_classify.py with the supports rebuilt on the GPU for every batch): designs the NEXT raw
+    batches (``synthetic.design_and_collate``: SpectralDesign of all graphs of a batch in one launch + collation) on side streams
+    while the current batch trains on the main stream.  At the reference's batch size (50 graphs) the one-block-per-graph Jacobi
+    is latency-bound (1.8 ms for 50 blocks on 148 SMs) and independent of the training step: ``depth`` designs in flight on
+    ``depth`` streams overlap with each other and with the step.  The raw tensors handed to ``prefetch`` must already be valid
+    on the device (the side streams do not wait for the main stream)."""
+
+    def __init__(self, sd, device, depth=2):
+        self.sd, self.device = sd, device
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        self._queue = []
+        self._k = 0
+
+    def prefetch(self, raw, records=False):
+        """``records=False``: a collated device ``Batch`` (``design_and_collate``); ``records=True``: the per-graph records of
+        ``synthetic.design_raw`` for ``GraphedTrainer.load_designed`` (collation + padding straight into the captured buffers)."""
+        from .synthetic import design_and_collate, design_raw
+        st = self.streams[self._k % len(self.streams)]
+        self._k += 1
+        with torch.cuda.stream(st):
+            b = design_raw(raw, self.sd, self.device) if records else design_and_collate(raw, self.sd, self.device)
+        ev = torch.cuda.Event()
+        ev.record(st)
+        self._queue.append((b, ev))
+
+    def pending(self):
+        return len(self._queue)
+
+    def get(self):
+        b, ev = self._queue.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        vals = list(b.values()) + list(b["design"].values()) if isinstance(b, dict) else list(b.__dict__.values())
+        for v in vals:
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                v.record_stream(cur)
+        return b
+
+
 def pad_batch(hb, n_nodes, n_entries):
     """Host ``Batch`` -> the same batch padded to ``n_nodes`` nodes and ``n_entries`` support entries (static shapes for CUDA
     graph replay).  The padding is exactly neutral: the extra nodes are isolated, carry zero features and form ONE extra
@@ -273,6 +313,16 @@ class GraphedTrainer(object):
         if N >= st.x.size(0) or cb.el.size(1) > st.edge_index2.size(1) or cb.num_graphs != self.real:
             raise ValueError("batch does not fit the captured shapes")
         cb.expand_into(st)
+
+    def load_designed(self, rec):
+        """Per-graph records of a batch whose supports were just designed on the GPU (``synthetic.design_raw``) -> the captured
+        input buffers: collation, global ids and the neutral padding in two library launches."""
+        from . import ops
+        d = rec["design"]
+        if rec["num_graphs"] != self.real:
+            raise ValueError("batch does not fit the captured shapes")
+        ops.collate_device(rec["n32"], d["counts"], d["edge_index2"], d["edge_attr2"], rec["num_graphs"], self.static, x=rec["x"])
+        self.static.y.copy_(rec["y"].reshape(self.static.y.shape), non_blocking=True)
 
     def load_from_dataset(self, dataset, idx_host):
         """Graph ids -> the captured input buffers, collated on the device from an HBM-resident ``DeviceDataset``."""

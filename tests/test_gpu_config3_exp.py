@@ -101,3 +101,52 @@ def test_exp_training_step_with_gpu_designed_supports():
         except AssertionError as e:          # a ReLU input within rounding distance of zero flips a mask (see test_gpu_model)
             msgs.append(str(e)[:200])
     assert ok, "gradients differ on every batch: " + " | ".join(msgs)
+
+
+def test_designed_records_into_captured_buffers_equal_the_collated_batch():
+    """Config 3 pipeline pieces (train.DesignFeeder / GraphedTrainer.load_designed): SpectralDesign with graph-local ids +
+    gnnml3_collate into padded static buffers == design_and_collate (global ids) padded by train.pad_batch, field by field; the
+    captured step on those buffers gives the eager loss."""
+    from gnn_matlang_b200.batch import Batch
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    from gnn_matlang_b200.models import GNNML3
+    from gnn_matlang_b200.synthetic import ExpPool, design_and_collate, design_raw
+    from gnn_matlang_b200.train import DesignFeeder, GraphedTrainer, Trainer, pad_batch
+    d = torch.device("cuda:0")
+    pool = ExpPool()
+    sd = SpectralDesign(recfield=1, dv=2, nfreq=5, adddegree=True)
+    rng = np.random.default_rng(3)
+    raws = [pool.draw_raw(rng, 20) for _ in range(3)]
+    raws = [{k: (v.to(d) if (isinstance(v, torch.Tensor) and k != "node_ptr") else v) for k, v in r.items()} for r in raws]
+    ref = [design_and_collate(r, sd, d) for r in raws]
+    Np = max(b.x.size(0) for b in ref) + 9
+    Ep = max(b.edge_index2.size(1) for b in ref) + 77
+    host0 = Batch(**{k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in ref[0].__dict__.items()})
+    torch.manual_seed(0)
+    m1 = GNNML3("exp", pool.K, pool.F).to(d)
+    torch.manual_seed(0)
+    m2 = GNNML3("exp", pool.K, pool.F).to(d)
+    gt = GraphedTrainer(m2, pad_batch(host0, Np, Ep), loss="bce", warmup=1)
+    with torch.no_grad():
+        for a, b in zip(m2.parameters(), m1.parameters()):
+            a.copy_(b)
+        for st in gt.opt.state.values():
+            for v in st.values():
+                if isinstance(v, torch.Tensor):
+                    v.zero_()
+    eager = Trainer(m1, loss="bce")
+    feeder = DesignFeeder(sd, d, depth=2)
+    for r in raws[:2]:
+        feeder.prefetch(r, records=True)
+    for i, r in enumerate(raws):
+        rec = feeder.get()
+        if i + 2 < len(raws):
+            feeder.prefetch(raws[i + 2], records=True)
+        gt.load_designed(rec)
+        hb = Batch(**{k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in ref[i].__dict__.items()})
+        want = pad_batch(hb, Np, Ep)
+        for k in ("x", "edge_index2", "edge_attr2", "batch", "graph_ptr"):
+            assert torch.equal(getattr(gt.static, k).cpu(), getattr(want, k)), (i, k)
+        l2 = float(gt.step())
+        l1 = float(eager.step(ref[i]))
+        assert abs(l1 - l2) <= 2e-5 * abs(l1), (i, l1, l2)
