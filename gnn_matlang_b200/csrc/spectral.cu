@@ -128,9 +128,13 @@ __device__ void jacobi_eigh(double* As, double* Us, int n, int ld, double* cs, d
                 if (q < n) {
                     const double apq = As[p * ld + q];
                     if (apq != 0.0) {
-                        const double theta = (As[q * ld + q] - As[p * ld + p]) / (2.0 * apq);
-                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = 1.0 / sqrt(t * t + 1.0);
+                        // t = sign(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = d / b, d = a_qq - a_pp, b = 2 a_pq, written
+                        // without forming theta:  t = sign(d b) |b| / (|d| + sqrt(d^2 + b^2)) -- one sqrt, one division and one
+                        // rsqrt on this serial chain of the round instead of three divisions and two square roots (the chain,
+                        // not the rotations, was the longest part of a round), and no overflow for tiny a_pq
+                        const double d = As[q * ld + q] - As[p * ld + p], b = 2.0 * apq;
+                        const double t = (((d >= 0.0) == (b >= 0.0)) ? 1.0 : -1.0) * fabs(b) / (fabs(d) + sqrt(d * d + b * b));
+                        c = rsqrt(t * t + 1.0);
                         s = t * c;
                     }
                 }
