@@ -12,6 +12,9 @@ echo "memcheck exit code: $?"
 timeout 420 compute-sanitizer --tool memcheck --error-exitcode 7 \
     python -m pytest tests/test_gpu_model.py -q -x -k "(edge_mlp or segment_pool) and not 70000 and $SEL"
 echo "memcheck (edge MLP, both generations) exit code: $?"
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 7 \
+    python -m pytest tests/test_gpu_data_path.py tests/test_gpu_spectral.py tests/test_gpu_config3_exp.py -q -x -k "$SEL"
+echo "memcheck (device collation, SpectralDesign, config 3) exit code: $?"
 timeout 300 compute-sanitizer --tool racecheck --error-exitcode 7 \
     python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -x -k "(edge_mlp or gemm_tn or segment_pool) and not 70000 and $SEL"
 echo "racecheck exit code: $?"
