@@ -63,18 +63,26 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_nn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
              const __grid_constant__ CUtensorMap mapBlo, const float* __restrict__ bias, float* __restrict__ C, int64_t ldc,
-             int64_t M, int Nc, int Kc, int epi, int chunk_kb, int n_mtiles) {
+             int64_t M, int Nc, int Kc, int epi, int chunk_kb, int n_mtiles, int b_res) {
     using Cfg = TCCfg<BN>;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * Cfg::STAGE_BYTES);
+    // b_res: the weight planes of this CTA's column block (all k-blocks, hi and lo) stay RESIDENT in shared memory and a stage
+    // carries the A tile only -- for the short contractions of the backward (dH = gc W^T: Kc = F) the planes are the same for
+    // every row tile, and re-fetching them per tile doubled the L2 -> shared-memory traffic the splitters wait for (ncu: 80 %
+    // of the splitter warps' time on `raw_full`)
+    const uint32_t stage_bytes = b_res ? 2u * TC_A_BYTES : (uint32_t)Cfg::STAGE_BYTES;
+    const int nkb_ = (Kc + TC_BK - 1) / TC_BK;
+    uint8_t* bres = smem + (size_t)TC_STAGES * stage_bytes;                           // [nkb][hi | lo] when b_res
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bres + (b_res ? (size_t)nkb_ * 2 * Cfg::B_BYTES : 0));
     uint64_t* raw_full = bars;                         // [STAGES]  TMA bytes landed              -> splitters
     uint64_t* full = bars + TC_STAGES;                 // [STAGES]  lo plane written              -> MMA
     uint64_t* empty = bars + 2 * TC_STAGES;            // [STAGES]  MMAs retired (tcgen05.commit) -> TMA
     uint64_t* tfull = bars + 3 * TC_STAGES;            // [NBUF]    accumulator chunk complete    -> epilogue
     uint64_t* tempty = bars + 3 * TC_STAGES + NBUF;    // [NBUF]    accumulator drained           -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 2 * NBUF);
+    uint64_t* bfull = bars + 3 * TC_STAGES + 2 * NBUF;   // resident weight planes landed           -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 2 * NBUF + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
@@ -90,6 +98,7 @@ k_gemm_nn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             mbar_init(tfull + b, 1);
             mbar_init(tempty + b, TC_EPILOGUE / 32);
         }
+        mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
@@ -105,16 +114,25 @@ k_gemm_nn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         // =================================================================== TMA producer (one lane)
         if (lane == 0) {
             uint32_t it = 0;
+            if (b_res) {
+                mbar_arrive_expect_tx(bfull, (uint32_t)nkb * 2u * Cfg::B_BYTES);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tma_load_2d(bres + (size_t)kb * 2 * Cfg::B_BYTES, &mapBhi, bfull, kb * TC_BK, n0);
+                    tma_load_2d(bres + (size_t)kb * 2 * Cfg::B_BYTES + Cfg::B_BYTES, &mapBlo, bfull, kb * TC_BK, n0);
+                }
+            }
             for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
                 const int m0 = tile * TC_BM;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     mbar_wait(empty + s, ((it / TC_STAGES) & 1) ^ 1);
-                    uint8_t* st = smem + (size_t)s * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(raw_full + s, Cfg::TX_BYTES);
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(raw_full + s, b_res ? (uint32_t)TC_A_BYTES : Cfg::TX_BYTES);
                     tma_load_2d(st, &mapA, raw_full + s, kb * TC_BK, m0);                                  // raw A (= hi)
-                    tma_load_2d(st + 2 * TC_A_BYTES, &mapBhi, raw_full + s, kb * TC_BK, n0);               // Bt_hi
-                    tma_load_2d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &mapBlo, raw_full + s, kb * TC_BK, n0); // Bt_lo
+                    if (!b_res) {
+                        tma_load_2d(st + 2 * TC_A_BYTES, &mapBhi, raw_full + s, kb * TC_BK, n0);               // Bt_hi
+                        tma_load_2d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &mapBlo, raw_full + s, kb * TC_BK, n0); // Bt_lo
+                    }
                 }
             }
         }
@@ -126,8 +144,8 @@ k_gemm_nn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % TC_STAGES;
                 mbar_wait(raw_full + s, (it / TC_STAGES) & 1);
-                const uint8_t* a_raw = smem + (size_t)s * Cfg::STAGE_BYTES;
-                uint8_t* a_lo = smem + (size_t)s * Cfg::STAGE_BYTES + TC_A_BYTES;
+                const uint8_t* a_raw = smem + (size_t)s * stage_bytes;
+                uint8_t* a_lo = smem + (size_t)s * stage_bytes + TC_A_BYTES;
 #pragma unroll
                 for (int j = 0; j < TC_A_BYTES / 16 / TC_SPLITTERS; ++j) {
                     const int off = (tid + TC_SPLITTERS * j) * 16;
@@ -149,6 +167,7 @@ k_gemm_nn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32<BN>();
             uint32_t it = 0, cc = 0;
+            if (b_res) mbar_wait(bfull, 0);
             for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t buf = cc % NBUF;
@@ -160,11 +179,12 @@ k_gemm_nn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     const int s = it % TC_STAGES;
                     mbar_wait(full + s, (it / TC_STAGES) & 1);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t sb = b_res ? smem_u32(bres + (size_t)kb * 2 * Cfg::B_BYTES) : sa + 2 * TC_A_BYTES;
                     const uint64_t da_hi = make_kmajor_sw128_desc(sa);
                     const uint64_t da_lo = make_kmajor_sw128_desc(sa + TC_A_BYTES);
-                    const uint64_t db_hi = make_kmajor_sw128_desc(sa + 2 * TC_A_BYTES);
-                    const uint64_t db_lo = make_kmajor_sw128_desc(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
+                    const uint64_t db_hi = make_kmajor_sw128_desc(sb);
+                    const uint64_t db_lo = make_kmajor_sw128_desc(sb + Cfg::B_BYTES);
                     const uint32_t d = tmem_base + buf * BN;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
@@ -270,8 +290,12 @@ static int launch_tc(const float* A, int64_t lda, const float* hi, const float* 
     int gx = kNumSMs / gy;
     if (gx < 1) gx = 1;
     if (gx > n_mtiles) gx = n_mtiles;
-    k_gemm_nn_tc<BN><<<dim3(gx, gy), TC_THREADS, Cfg::SMEM, st>>>(mapA, mapBhi, mapBlo, bias, C, ldc, M, Nc, Kc, epi, chunk_kb,
-                                                                  n_mtiles);
+    // resident weight planes when they fit beside the four A stages and every CTA walks more than a few row tiles
+    const int nkb = cdiv(Kc, TC_BK);
+    const size_t res_smem = (size_t)TC_STAGES * 2 * TC_A_BYTES + (size_t)nkb * 2 * Cfg::B_BYTES + 1024 + 512;
+    const int b_res = (res_smem <= Cfg::SMEM && n_mtiles >= 4 * gx) ? 1 : 0;
+    k_gemm_nn_tc<BN><<<dim3(gx, gy), TC_THREADS, b_res ? res_smem : Cfg::SMEM, st>>>(mapA, mapBhi, mapBlo, bias, C, ldc, M, Nc, Kc, epi,
+                                                                                   chunk_kb, n_mtiles, b_res);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
