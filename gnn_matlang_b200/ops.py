@@ -346,13 +346,29 @@ def ml3_act_bwd(pre, gy, Fo, G, gate_out=None):
     return gpre, csum
 
 
+def _padded_rows(N, W, device):
+    """[N, W] float32 view of a buffer whose rows are padded to a multiple of 4 floats, padding columns zeroed (they are read,
+    and multiplied by zero weights, by the next fused gather); the base carries the mark ``aligned_rows`` looks for."""
+    ld = (W + 3) // 4 * 4
+    buf = torch.empty(N, ld, dtype=torch.float32, device=device)
+    if ld != W:
+        buf[:, W:].zero_()
+        buf._gnnml3_zero_pad = True
+        return buf[:, :W]
+    return buf
+
+
 def aligned_rows(t):
     """float32 CUDA matrix with unit column stride, row stride % 4 == 0 and a 16-byte aligned base (what the 128-bit
     gathers of the fused kernels need); otherwise a zero-padded copy [N, ceil4(F)] (data movement only)."""
     if t.dtype != torch.float32 or not t.is_cuda:
         raise RuntimeError("expected a float32 CUDA tensor: gnn_matlang_b200 has no CPU fallback")
     if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 and t.stride(0) >= t.size(1):
-        return t
+        # F % 4 != 0: the kernels gather ceil4(F) columns and rely on zero weights for the padding -- 0 * NaN is NaN, so a view
+        # passes through only when its padding columns are known to be zero (tensors allocated by _padded_rows below); a
+        # caller's column block of a wider matrix is copied
+        if t.size(1) % 4 == 0 or getattr(t._base, "_gnnml3_zero_pad", False):
+            return t
     N, F = t.shape
     buf = torch.zeros(N, (F + 3) // 4 * 4, dtype=torch.float32, device=t.device)
     buf[:, :F] = t
@@ -388,11 +404,7 @@ def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mod
             raise RuntimeError("fused_agg_proj: Bself must have %d rows" % Fs)
     dev = x.device
     W = Nc + (G if self_mode == 1 else 0)
-    ldo = (W + 3) // 4 * 4
-    out = torch.empty(N, ldo, dtype=torch.float32, device=dev)
-    if ldo != W:
-        out[:, W:].zero_()          # padding columns are read (and multiplied by zero weights) by the next fused gather
-    out = out[:, :W]
+    out = _padded_rows(N, W, dev)
     aux = torch.empty(N, 2 * G, dtype=torch.float32, device=dev) if self_mode == 1 else None
     if bias is not None:
         bias = _f32c(bias, "bias")
@@ -408,7 +420,7 @@ def fused_agg_proj(rowptr, col, eperm, ea, x, Bmain, bias=None, S=None, self_mod
             _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(eperm), _lib.ptr(ea), K, K, _lib.ptr(x), _ld(x), F,
             _lib.ptr(S) if self_mode else None, _ld(S) if self_mode else 0, Fs, self_mode, _lib.ptr(Bmain), _ld(Bmain),
             _lib.ptr(Bself) if self_mode else None, _ld(Bself) if self_mode else 0, Ns, _lib.ptr(bias), _lib.ptr(bias_s),
-            N, Nc, _lib.ptr(out), ldo, _lib.ptr(aux), 2 * G, G, epilogue | _lib.FUSED_FLAGS[precision], _lib.ptr(hout), _ld(hout) if hout is not None else 0,
+            N, Nc, _lib.ptr(out), (W + 3) // 4 * 4, _lib.ptr(aux), 2 * G, G, epilogue | _lib.FUSED_FLAGS[precision], _lib.ptr(hout), _ld(hout) if hout is not None else 0,
             _lib.ptr(win), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
             "gnnml3_fused_agg_proj")
     return out, aux
@@ -493,10 +505,8 @@ def ml3layer_forward(plan, x, ea_s, ws4, wconv, bconv, gates):
     G = gates[0].size(0) if gates is not None else 0
     dev = x.device
     W = Fo + G
+    y = _padded_rows(N, W, dev)
     ldy = (W + 3) // 4 * 4
-    y = torch.empty(N, ldy, dtype=torch.float32, device=dev)
-    if ldy != W:
-        y[:, W:].zero_()
     aux = torch.empty(N, 2 * G, dtype=torch.float32, device=dev) if G > 0 else None
     ea2 = torch.empty(E, K, dtype=torch.float32, device=dev) if ws4 is not None else None
     ws = _ws(dev, lib.gnnml3_ml3layer_workspace_bytes(N, E, K, Fi, Fo, G), tag="layer")
@@ -507,7 +517,7 @@ def ml3layer_forward(plan, x, ea_s, ws4, wconv, bconv, gates):
         _lib.check(lib.gnnml3_ml3layer_forward(p(plan.rowptr), p(plan.col), p(plan.win), N, E, p(x), _ld(x), Fi, p(ea_s), K, p(w[0]), p(w[1]), p(w[2]),
                                                p(w[3]), p(wconv), p(bconv), Fo, p(g[0]), p(g[1]), p(g[2]), p(g[3]), G, p(ea2), p(y), ldy,
                                                p(aux), p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_forward")
-    return y[:, :W], aux, ea2
+    return y, aux, ea2
 
 
 def ml3layer_backward(plan, x, ea_s, ea2, ws4, wconv, gates_w, y, aux, gy, need_dx, need_dea, has_bias):

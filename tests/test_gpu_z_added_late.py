@@ -163,3 +163,37 @@ def test_full_size_adjoint_and_linearity_properties(case):
     ref = 0.75 * y1.detach().double() - 1.5 * y2.double()
     err = (y3.double() - ref).abs().max().item()
     assert err <= 2e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+def test_aligned_rows_copies_foreign_column_blocks():
+    """ADVICE (round 1): a caller's column-block view with F % 4 != 0 whose neighbouring columns hold NaN must not reach the
+    128-bit gathers as it is (the kernels multiply the padding columns by zero weights, and 0 * NaN is NaN); tensors the
+    library allocated itself (zeroed padding) still pass through without a copy."""
+    from gnn_matlang_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    N, F, K, Nc, deg = 3000, 30, 8, 16, 5
+    wide = torch.full((N, 32), float("nan"))
+    wide[:, :F] = torch.randn(N, F, generator=g)
+    xv = wide.to(dev())[:, :F]
+    assert xv.stride(0) == 32 and xv.data_ptr() % 16 == 0
+    xa = ops.aligned_rows(xv)
+    assert xa.data_ptr() != xv.data_ptr(), "a foreign view with F % 4 != 0 must be copied"
+    src = torch.randint(0, N, (N * deg,), generator=g)
+    dst = torch.randint(0, N, (N * deg,), generator=g)
+    ei = torch.stack([src, dst])
+    ea = torch.randn(N * deg, K, generator=g)
+    W = torch.randn(K, F, Nc, generator=g) / np.sqrt(K * F)
+    plan = ops.csr_build(ei.to(dev()), N)
+    ea_s = ea.to(dev())[plan["perm"].long()].contiguous()
+    out, _ = ops.fused_agg_proj(plan["rowptr"], plan["col"], None, ea_s, xa, W.view(K * F, Nc).to(dev()), epilogue=0)   # global gathers
+    ref = torch.zeros(N, Nc, dtype=torch.float64)
+    x64 = wide[:, :F].double()
+    for k in range(K):
+        ref += torch.zeros(N, F, dtype=torch.float64).index_add_(0, dst, ea[:, k:k + 1].double() * x64[src]) @ W[k].double()
+    assert bool(torch.isfinite(out).all())
+    assert_close(out, ref, name="conv on a copied column block")
+    # library-allocated padded rows: no copy, and the same tensor goes straight into the next gather
+    y, _ = ops.fused_agg_proj(plan["rowptr"], plan["col"], None, ea_s, xa, torch.randn(K * F, 30, generator=g).to(dev()), epilogue=0)
+    assert y.size(1) == 30 and y.stride(0) == 32
+    assert ops.aligned_rows(y).data_ptr() == y.data_ptr()
+    assert float(y._base[:, 30:].abs().max()) == 0.0
