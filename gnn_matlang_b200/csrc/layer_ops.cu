@@ -8,6 +8,8 @@
 //                 sum in node order, no atomics.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gnnml3 {
 
 __global__ void k_ml3_act_fwd(const float* __restrict__ pre, int64_t ldp, int64_t N, int Fo, int G, float* __restrict__ y,
@@ -171,6 +173,138 @@ k_ml3_act_bwd_y(const float* __restrict__ y, int64_t ldy, const float* __restric
                 float t = 0.f;
                 for (int g2 = 0; g2 < nseg; ++g2) t += seg_sum[g2 * ld + cc];      // fixed order: deterministic
                 colpart[(int64_t)blockIdx.x * W2 + lc] = t;
+            }
+        }
+    }
+}
+
+// Streaming form of k_ml3_act_bwd_y for the aligned shapes of the GNNML3 layers (Fo4 = 4 GCV floats with GCV a power of two,
+// gate width 2 or a multiple of 4): a thread keeps ONE 4-column group and walks the block's rows with a fixed stride, so
+//   * all of its 128-bit loads are independent and issued before the first use (the general kernel recomputes (row, group)
+//     by a division per element and kept ~4 loads in flight: 2.3 TB/s),
+//   * the column sums accumulate in registers (no shared-memory tile, no second pass over it): shuffle tree over the lanes
+//     that share the group, then the eight warps in fixed order -- deterministic.
+// Same values in gpre bit for bit (same expressions); same per-block partial layout, finished by k_colsum_finish.
+template <int GCV>
+__global__ void __launch_bounds__(256)
+k_ml3_act_bwd_y_v(const float* __restrict__ y, int64_t ldy, const float* __restrict__ aux, int64_t ldaux,
+                  const float* __restrict__ gy, int64_t ldgy, int64_t N, int Fo, int G, float* __restrict__ gpre, int64_t ldg,
+                  float* __restrict__ colpart) {
+    constexpr int RPP = 256 / GCV;                  // rows per pass of the conv block
+    constexpr int NPASS = ACTY_ROWS / RPP;          // = GCV / 2
+    __shared__ float red[8][68];
+    const int Fo4 = 4 * GCV, W2 = Fo + 2 * G;
+    const int64_t r0 = (int64_t)blockIdx.x * ACTY_ROWS;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    // ---- conv block: d pre = (y > 0) ? gy : 0
+    {
+        const int cg = t % GCV, rl0 = t / GCV, c = 4 * cg;
+        float4 yy[NPASS], gg[NPASS];
+#pragma unroll
+        for (int j = 0; j < NPASS; ++j) {
+            const int64_t n = r0 + rl0 + j * RPP;
+            if (n < N) {
+                yy[j] = ldg4(y + n * ldy + c);
+                gg[j] = ldg4(gy + n * ldgy + c);
+            }
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NPASS; ++j) {
+            const int64_t n = r0 + rl0 + j * RPP;
+            if (n < N) {
+                float4 o;
+                o.x = yy[j].x > 0.f ? gg[j].x : 0.f;
+                o.y = (c + 1 < Fo && yy[j].y > 0.f) ? gg[j].y : 0.f;
+                o.z = (c + 2 < Fo && yy[j].z > 0.f) ? gg[j].z : 0.f;
+                o.w = (c + 3 < Fo && yy[j].w > 0.f) ? gg[j].w : 0.f;
+                if (c >= Fo) o.x = 0.f;
+                *reinterpret_cast<float4*>(gpre + n * ldg + c) = o;
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+        }
+        if (colpart) {
+#pragma unroll
+            for (int o = GCV; o < 32; o <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+            if (GCV >= 32 || lane < GCV) *reinterpret_cast<float4*>(&red[warp][4 * (lane % GCV)]) = acc;
+            __syncthreads();
+            if (t < Fo) {
+                float v = 0.f;
+                if (GCV < 32) {
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) v += red[w][t];
+                }
+                colpart[(int64_t)blockIdx.x * W2 + t] = v;
+            }
+            __syncthreads();
+        }
+    }
+    // ---- gate block: [g1 | g2] at columns Fo4 .. Fo4 + 2G
+    if (G == 2) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t n = r0 + t;
+        if (t < ACTY_ROWS && n < N) {
+            const float4 tt = ldg4(aux + n * ldaux);                    // t1_0 t1_1 t2_0 t2_1
+            const float g0 = __ldg(gy + n * ldgy + Fo), g1 = __ldg(gy + n * ldgy + Fo + 1);
+            o.x = g0 * tt.z * (1.f - tt.x * tt.x);
+            o.y = g1 * tt.w * (1.f - tt.y * tt.y);
+            o.z = g0 * tt.x * (1.f - tt.z * tt.z);
+            o.w = g1 * tt.y * (1.f - tt.w * tt.w);
+            *reinterpret_cast<float4*>(gpre + n * ldg + Fo4) = o;
+        }
+        if (colpart) {
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                o.x += __shfl_xor_sync(0xffffffffu, o.x, s);
+                o.y += __shfl_xor_sync(0xffffffffu, o.y, s);
+                o.z += __shfl_xor_sync(0xffffffffu, o.z, s);
+                o.w += __shfl_xor_sync(0xffffffffu, o.w, s);
+            }
+            if (lane == 0 && warp < 4) *reinterpret_cast<float4*>(&red[warp][0]) = o;
+            __syncthreads();
+            if (t < 4) colpart[(int64_t)blockIdx.x * W2 + Fo + t] = ((red[0][t] + red[1][t]) + red[2][t]) + red[3][t];
+        }
+    } else if (G > 0) {
+        // G % 4 == 0, Fo % 4 == 0: GG = G / 2 groups per row (a power of two <= 16), the first G / 4 belong to g1
+        const int GG = G >> 1, rpp = 256 / GG, npass = ACTY_ROWS / rpp;
+        const int gi = t % GG, rl0 = t / GG;
+        const int second = gi >= (G >> 2) ? 1 : 0, j0 = 4 * (gi - second * (G >> 2));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < npass; ++j) {
+            const int64_t n = r0 + rl0 + j * rpp;
+            if (n < N) {
+                const float4 g = ldg4(gy + n * ldgy + Fo + j0), t1 = ldg4(aux + n * ldaux + j0), t2 = ldg4(aux + n * ldaux + G + j0);
+                float4 o;
+                if (second) {
+                    o.x = g.x * t1.x * (1.f - t2.x * t2.x); o.y = g.y * t1.y * (1.f - t2.y * t2.y);
+                    o.z = g.z * t1.z * (1.f - t2.z * t2.z); o.w = g.w * t1.w * (1.f - t2.w * t2.w);
+                } else {
+                    o.x = g.x * t2.x * (1.f - t1.x * t1.x); o.y = g.y * t2.y * (1.f - t1.y * t1.y);
+                    o.z = g.z * t2.z * (1.f - t1.z * t1.z); o.w = g.w * t2.w * (1.f - t1.w * t1.w);
+                }
+                *reinterpret_cast<float4*>(gpre + n * ldg + Fo4 + 4 * gi) = o;
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+        }
+        if (colpart) {
+            for (int s = GG; s < 32; s <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, s);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, s);
+            }
+            if (lane < GG) *reinterpret_cast<float4*>(&red[warp][4 * lane]) = acc;
+            __syncthreads();
+            if (t < 2 * G) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += red[w][t];
+                colpart[(int64_t)blockIdx.x * W2 + Fo + t] = v;
             }
         }
     }
@@ -375,7 +509,15 @@ extern "C" int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* au
     GNNML3_REQUIRE(ldg % 4 == 0 && (uintptr_t)gpre % 16 == 0, "ml3_act_bwd_y: gpre rows must be 16-byte aligned");
     const int nb = cdiv(N, ACTY_ROWS);
     const int vec_in = (ldy % 4 == 0 && ldgy % 4 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)gy % 16 == 0) ? 1 : 0;
-    k_ml3_act_bwd_y<<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, vec_in);
+    // streaming kernel for the aligned layer shapes (every GNNML3 configuration); the general kernel for the rest
+    const bool gates_ok = G == 0 || (G == 2 && ldaux % 4 == 0 && ((uintptr_t)aux & 15) == 0) ||
+                          (G % 4 == 0 && (G & (G - 1)) == 0 && G <= 32 && Fo % 4 == 0 && ldaux % 4 == 0 && ((uintptr_t)aux & 15) == 0);
+    static const bool general_only = [] { const char* e = getenv("GNNML3_ACT_GENERAL"); return e && e[0] == '1'; }();   // measurement switch
+    const bool fast = !general_only && vec_in && gates_ok && ldg == Fo4 + 2 * G && (Fo4 == 16 || Fo4 == 32 || Fo4 == 64) && ldy >= Fo4 && ldgy >= Fo4;
+    if (fast && Fo4 == 16) k_ml3_act_bwd_y_v<4><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part);
+    else if (fast && Fo4 == 32) k_ml3_act_bwd_y_v<8><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part);
+    else if (fast) k_ml3_act_bwd_y_v<16><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part);
+    else k_ml3_act_bwd_y<<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, vec_in);
     GNNML3_LAUNCH_CHECK();
     if (colsum) {
         k_colsum_finish<<<cdiv(Fo + 2 * G, 8), 256, 0, st>>>(part, nb, Fo + 2 * G, colsum);

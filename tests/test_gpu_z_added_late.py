@@ -197,3 +197,31 @@ def test_aligned_rows_copies_foreign_column_blocks():
     assert y.size(1) == 30 and y.stride(0) == 32
     assert ops.aligned_rows(y).data_ptr() == y.data_ptr()
     assert float(y._base[:, 30:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,Fo,G", [(1000, 30, 2), (129, 32, 16), (5000, 16, 16), (777, 64, 0), (300, 13, 4), (2000, 32, 8), (640, 30, 0)])
+def test_act_bwd_y_streaming_and_general_kernels(N, Fo, G):
+    """d pre and the bias sums from the fused layer's outputs: the streaming kernel (aligned shapes: Fo4 in {16, 32, 64}, gate
+    width 2 or a power-of-two multiple of 4 with Fo % 4 == 0) and the general kernel (everything else) against float64 autograd."""
+    from gnn_matlang_b200 import ops
+    g = torch.Generator().manual_seed(N + Fo + G)
+    pre = torch.randn(N, Fo + 2 * G, generator=g)
+    gy = torch.randn(N, Fo + G, generator=g)
+    y = torch.cat([torch.relu(pre[:, :Fo]), torch.tanh(pre[:, Fo:Fo + G]) * torch.tanh(pre[:, Fo + G:])], 1)
+    aux = torch.tanh(pre[:, Fo:])
+    d = dev()
+    W = Fo + G
+    ld = (W + 3) // 4 * 4
+    yb = torch.zeros(N, ld); yb[:, :W] = y
+    gb = torch.zeros(N, ld); gb[:, :W] = gy
+    gpre, csum = ops.ml3_act_bwd_y(yb.to(d)[:, :W], aux.to(d) if G else None, gb.to(d)[:, :W], Fo, G)
+    pr = pre.double().requires_grad_(True)
+    yr = torch.cat([torch.relu(pr[:, :Fo]), torch.tanh(pr[:, Fo:Fo + G]) * torch.tanh(pr[:, Fo + G:])], 1)
+    yr.backward(gy.double())
+    Fo4 = (Fo + 3) // 4 * 4
+    assert_close(gpre[:, :Fo], pr.grad[:, :Fo], name="gc")
+    if G:
+        assert_close(gpre[:, Fo4:Fo4 + 2 * G], pr.grad[:, Fo:], name="gates")
+    if Fo4 > Fo:
+        assert float(gpre[:, Fo:Fo4].abs().max()) == 0.0
+    assert_close(csum, pr.grad.sum(0), name="bias sums")
