@@ -414,23 +414,31 @@ bool gemm_tn_tc_ok(const float* A, int64_t lda, const float* B, int64_t ldb, int
 int gemm_tn_tc_parts(int64_t M);
 int gemm_tn_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* P, int64_t M, int Ka, int Nb, cudaStream_t st);
 
-// C[i] = sum_z P[z][i] in a fixed order: 8 split-lanes per output accumulate strided partial sums, then a fixed tree
-__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ P, int splits, int64_t n, int cols,
-                                                         float* __restrict__ C, int64_t ldc) {
-    __shared__ float red[8][33];
+// C[i] = sum_z P[z][i] in a fixed order: TY split-lanes per output accumulate strided partial sums, then a fixed tree.
+// TY = 8 for wide outputs (many blocks); TY = 32 when a few outputs are summed over hundreds of partials (the bias sums and
+// the narrow weight gradients: 128 outputs x 740 partials ran as 4 blocks of 92 dependent loads per thread, 16 us)
+template <int TY>
+__global__ void __launch_bounds__(32 * TY) k_reduce_partials(const float* __restrict__ P, int splits, int64_t n, int cols,
+                                                            float* __restrict__ C, int64_t ldc) {
+    __shared__ float red[TY][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * 32 + tx;
     float s = 0.f;
     if (i < n)
-        for (int z = ty; z < splits; z += 8) s += __ldg(P + (int64_t)z * n + i);
+        for (int z = ty; z < splits; z += TY) s += __ldg(P + (int64_t)z * n + i);
     red[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && i < n) {
         float v = 0.f;
 #pragma unroll
-        for (int y = 0; y < 8; ++y) v += red[y][tx];
+        for (int y = 0; y < TY; ++y) v += red[y][tx];
         C[(i / cols) * ldc + (i % cols)] = v;
     }
+}
+static inline void launch_reduce_partials(const float* P, int splits, int64_t n, int cols, float* C, int64_t ldc, cudaStream_t st) {
+    const int blocks = cdiv(n, 32);
+    if (splits >= 128 && blocks <= 2 * kNumSMs) k_reduce_partials<32><<<blocks, 1024, 0, st>>>(P, splits, n, cols, C, ldc);
+    else k_reduce_partials<8><<<blocks, 256, 0, st>>>(P, splits, n, cols, C, ldc);
 }
 
 static inline int tn_ba_for(int Ka) { return Ka <= 32 ? 32 : 64; }
@@ -578,7 +586,7 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
         k_gemm_tn_narrow<<<(unsigned)nblk, TNN_WARPS * 32, 0, st>>>(A, lda, B, ldb, P, M, Ka, Nb);
         GNNML3_LAUNCH_CHECK();
         const int64_t n = (int64_t)Ka * Nb;
-        k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, (int)nblk, n, Nb, C, ldc);
+        launch_reduce_partials(P, (int)nblk, n, Nb, C, ldc, st);
         GNNML3_LAUNCH_CHECK();
         return GNNML3_OK;
     }
@@ -594,7 +602,7 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
                 const int nbc = Nb - c0 < 256 ? Nb - c0 : 256;
                 if ((rc = gemm_tn_tc_launch(A + a0, lda, B + c0, ldb, P, M, kac, nbc, st))) return rc;
                 const int64_t n = (int64_t)kac * nbc;
-                k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, gemm_tn_tc_parts(M), n, nbc, C + (int64_t)a0 * ldc + c0, ldc);
+                launch_reduce_partials(P, gemm_tn_tc_parts(M), n, nbc, C + (int64_t)a0 * ldc + c0, ldc, st);
                 GNNML3_LAUNCH_CHECK();
             }
         }
@@ -611,7 +619,7 @@ extern "C" int gnnml3_gemm_tn(const float* A, int64_t lda, const float* B, int64
                 : launch_tn_v<64, 64, false>(va, vb, A, lda, B, ldb, P, M, Ka, Nb, splits, rps, st);
     if (rc) return rc;
     const int64_t n = (int64_t)Ka * Nb;
-    k_reduce_partials<<<cdiv(n, 32), 256, 0, st>>>(P, splits, n, Nb, C, ldc);
+    launch_reduce_partials(P, splits, n, Nb, C, ldc, st);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
@@ -629,7 +637,7 @@ extern "C" int gnnml3_colsum(const float* A, int64_t lda, int64_t M, int Nc, flo
     const int nb = cdiv(M, CS_ROWS);
     k_colsum_partial<<<nb, 256, 0, st>>>(A, lda, M, Nc, (float*)workspace);
     GNNML3_LAUNCH_CHECK();
-    k_reduce_partials<<<cdiv(Nc, 32), 256, 0, st>>>((const float*)workspace, nb, Nc, Nc, out, Nc);
+    launch_reduce_partials((const float*)workspace, nb, Nc, Nc, out, Nc, st);
     GNNML3_LAUNCH_CHECK();
     return GNNML3_OK;
 }
