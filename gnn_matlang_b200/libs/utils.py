@@ -7,7 +7,10 @@
 Same constructor arguments and the same ``__call__(data) -> data`` contract, plus a batched entry point
 (``design_batch``) that designs the supports of many graphs in one launch -- one CUDA thread block per graph,
 FP64 Jacobi eigensolver in shared memory (the reference loops over graphs in Python with one dense numpy
-``eigh`` each).  The PPGN tensors ``X2`` / ``M`` that the reference also builds when ``nmax > 0``
+``eigh`` each).  Graphs beyond the shared-memory envelope of that kernel (more than ``gnnml3_spectral_max_nodes`` nodes:
+the single 900-node grid of ``filtering.py:17``) take a dense device path (``_design_large``: cuSOLVER ``eigh`` + dense
+products through torch, still no CPU arithmetic) -- outside the north-star's "small symmetric Laplacians", kept so that the
+reference's script finds its transform.  The PPGN tensors ``X2`` / ``M`` that the reference also builds when ``nmax > 0``
 (:613-624) are not read by GNNML3 and are not produced (``nmax`` is accepted and ignored).
 No CPU fallback: a CUDA device is required.
 """
@@ -100,9 +103,75 @@ class SpectralDesign(object):
                 _lib.ptr(ei2), E2, _lib.ptr(ea2), _lib.ptr(lmax), _lib.ptr(deg), st), "gnnml3_spectral_design")
         return dict(edge_index2=ei2, edge_attr2=ea2, e2_ptr=e2_ptr, counts=counts, lmax=lmax, degree=deg)
 
+    # ------------------------------------------------------------------------------------------ one large graph
+    def max_kernel_nodes(self):
+        """Largest graph the one-block-per-graph kernel designs (its Jacobi lives in shared memory)."""
+        return int(_lib.load().gnnml3_spectral_max_nodes(int(self.nfreq)))
+
+    def _design_large(self, edge_index, n, device=None):
+        """One graph of more than ``max_kernel_nodes()`` nodes, dense on the device (libs/utils.py:558-610 restated with
+        torch ops: FP64 ``torch.linalg.eigh`` = cuSOLVER for the Laplacian, the reference's float32 ``eigh(A)`` when
+        ``laplacien=False``).  Same outputs as ``design_batch`` with B = 1; the mask is binarised after every squaring (same
+        pattern as the reference's ``(A + I)^(2^(r-1)) > 0``: all entries are non-negative)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("gnn_matlang_b200.SpectralDesign needs a CUDA device (no CPU fallback)")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        ei = torch.as_tensor(edge_index).reshape(2, -1).to(device=device, dtype=torch.int64)
+        f64 = dict(dtype=torch.float64, device=device)
+        A = torch.zeros(n, n, dtype=torch.float32, device=device)
+        A[ei[0], ei[1]] = 1.0                                                     # :558-560
+        deg = A.sum(0)                                                            # column sums (:563, :576)
+        eye = torch.eye(n, **f64)
+        if self.recfield == 0:                                                    # :566-573
+            M = A > 0
+        else:
+            M = (A.double() + eye) > 0
+            for _ in range(1, int(self.recfield)):
+                Md = M.double()
+                M = (Md @ Md) > 0
+        dis = 1.0 / deg.sqrt()
+        dis = torch.where(torch.isfinite(dis), dis, torch.zeros_like(dis))        # :578-580
+        AD = A * dis[None, :]                                                     # float32 products as in the reference (:582)
+        nL = eye - (AD.t() * dis[None, :]).double()
+        V, U = torch.linalg.eigh(nL)                                              # :583-584
+        V = V.clamp_min(0.0)
+        lmax = V.max().to(torch.float32)                                          # :586
+        if not self.laplacien:                                                    # :588-589 (float32, unclamped)
+            V, U = torch.linalg.eigh(A)
+            V, U = V.double(), U.double()
+        top = V.max() if self.vmax is None else torch.tensor(float(self.vmax), **f64)          # :592-596
+        lo = V.min()
+        nf = int(self.nfreq)
+        centers = [lo + (top - lo) * (i / (nf - 1)) if nf > 1 else lo for i in range(nf)]       # np.linspace(V.min(), vmax, nfreq)
+        r, c = torch.nonzero(M, as_tuple=True)                                    # row-major, as np.where (:608)
+        K = self.num_supports
+        ea2 = torch.zeros(r.numel(), K, dtype=torch.float32, device=device)
+        for i in range(nf):                                                       # :599-600
+            S = (U * torch.exp(-(float(self.dv) * (V - centers[i]) ** 2))[None, :]) @ U.t()
+            ea2[:, i] = S[r, c].to(torch.float32)
+        ea2[:, nf] = (r == c).to(torch.float32)                                   # identity support (:602)
+        if self.addadj:
+            ea2[:, nf + 1] = A[r, c]                                              # :604-605
+        e2_ptr = torch.tensor([0, r.numel()], dtype=torch.int64, device=device)
+        return dict(edge_index2=torch.stack([r, c]), edge_attr2=ea2, e2_ptr=e2_ptr,
+                    counts=torch.tensor([r.numel()], dtype=torch.int32, device=device), lmax=lmax.reshape(1), degree=deg)
+
     def design_list(self, graphs, device=None):
         """``graphs``: list of (n, edge_index [2,e]) pairs -> per-graph list of dicts (edge_index2, edge_attr2,
         lmax, degree), all designed in one launch."""
+        limit = self.max_kernel_nodes()
+        if any(int(n) > limit for n, _ in graphs):
+            # graphs beyond the kernel's envelope one by one on the dense path, the rest in one launch
+            small = [(i, g) for i, g in enumerate(graphs) if int(g[0]) <= limit]
+            res = [None] * len(graphs)
+            for (i, _), r in zip(small, self.design_list([g for _, g in small], device=device) if small else []):
+                res[i] = r
+            for i, (n, e) in enumerate(graphs):
+                if int(n) > limit:
+                    o = self._design_large(np.asarray(e, dtype=np.int64), int(n), device=device)
+                    res[i] = dict(edge_index2=o["edge_index2"], edge_attr2=o["edge_attr2"], lmax=o["lmax"][0], degree=o["degree"])
+            return res
         ns = np.array([int(n) for n, _ in graphs], dtype=np.int64)
         es = np.array([int(np.asarray(e).shape[1]) for _, e in graphs], dtype=np.int64)
         node_ptr = np.concatenate([[0], np.cumsum(ns)])
@@ -122,7 +191,10 @@ class SpectralDesign(object):
         src_dev = data.x.device
         data.x = data.x.type(torch.float32)
         ei = data.edge_index
-        out = self.design_batch(ei.reshape(2, -1), torch.tensor([0, ei.reshape(2, -1).shape[1]]), torch.tensor([0, n]))
+        if n > self.max_kernel_nodes():
+            out = self._design_large(ei, n)
+        else:
+            out = self.design_batch(ei.reshape(2, -1), torch.tensor([0, ei.reshape(2, -1).shape[1]]), torch.tensor([0, n]))
         if self.adddegree:
             data.x = torch.cat([data.x, out["degree"].to(src_dev).unsqueeze(-1)], 1)
         data.lmax = np.float32(out["lmax"][0].item())

@@ -99,10 +99,49 @@ def test_spectral_design_global_ids_equal_collation():
     assert np.all(np.abs(got - ref_ea) <= 1e-4 * np.abs(ref_ea) + 1e-4 * np.abs(ref_ea).max())
 
 
-def test_spectral_design_rejects_oversized_graphs():
+def test_spectral_design_batched_kernel_rejects_oversized_graphs():
+    """The one-block-per-graph kernel names its envelope instead of computing garbage; `__call__` / `design_list` route such
+    graphs to the dense device path (next test)."""
     from gnn_matlang_b200.libs.utils import SpectralDesign
     n = 200
     ei = np.vstack((np.arange(n - 1), np.arange(1, n)))
     ei = np.concatenate([ei, ei[::-1]], 1)
     with pytest.raises(RuntimeError, match="nodes"):
-        SpectralDesign().design_list([(n, ei)])
+        SpectralDesign().design_batch(torch.from_numpy(ei), torch.tensor([0, ei.shape[1]]), torch.tensor([0, n]))
+
+
+def _grid(side):
+    idx = np.arange(side * side).reshape(side, side)
+    e = np.concatenate([np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()]), np.stack([idx[:-1, :].ravel(), idx[1:, :].ravel()])], 1)
+    return side * side, np.concatenate([e, e[::-1]], 1)
+
+
+@pytest.mark.parametrize("side,kw", [(30, dict(recfield=5, dv=10, nfreq=10, adddegree=False)),          # filtering.py:17
+                                     (14, dict(recfield=2, dv=5, nfreq=5, adddegree=True, addadj=True)),
+                                     (13, dict(recfield=1, dv=2, nfreq=4, laplacien=False, vmax=3.0))])
+def test_spectral_design_large_graph_dense_path(side, kw):
+    """Graphs beyond the shared-memory eigensolver (the 900-node 2-D grid of filtering.py:17, `nmax=900, recfield=5, dv=10,
+    nfreq=10`): `__call__` designs them on the dense device path; mask bit-exact, supports as matrices within rtol 1e-4 of the
+    oracle (the grid's Laplacian has many degenerate eigenvalues: only the matrices are comparable)."""
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    n, ei = _grid(side)
+    sd = SpectralDesign(nmax=n, **kw)
+    assert n > sd.max_kernel_nodes()
+    d = _Data()
+    d.x = torch.ones(n, 1)
+    d.edge_index = torch.from_numpy(ei)
+    out = sd(d)
+    with np.errstate(all="ignore"):
+        ref = O.spectral_design(ei, np.ones((n, 1), np.float32), **kw)
+    assert np.array_equal(out.edge_index2.numpy(), ref["edge_index2"])
+    assert np.array_equal(out.x.numpy(), ref["x"])
+    _close_supports(out.edge_index2.numpy(), out.edge_attr2.numpy(), ref["edge_index2"], ref["edge_attr2"], n)
+    np.testing.assert_allclose(out.lmax, ref["lmax"], rtol=1e-5, atol=1e-6)
+    # mixed list: the small graph goes through the kernel, the large one through the dense path
+    n2, ei2 = _grid(5)
+    res = sd.design_list([(n2, ei2), (n, ei)])
+    assert np.array_equal(res[1]["edge_index2"].cpu().numpy(), ref["edge_index2"])
+    with np.errstate(all="ignore"):
+        ref2 = O.spectral_design(ei2, np.ones((n2, 1), np.float32), **kw)
+    assert np.array_equal(res[0]["edge_index2"].cpu().numpy(), ref2["edge_index2"])
+    _close_supports(res[0]["edge_index2"].cpu().numpy(), res[0]["edge_attr2"].cpu().numpy(), ref2["edge_index2"], ref2["edge_attr2"], n2)
