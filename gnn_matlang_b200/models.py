@@ -13,6 +13,8 @@ concatenated read-outs, log-softmax heads:
                                           BatchNorm1d(128), log_softmax(fc2 -> 6)
 * ``mutag``    -- mutag.py:268-307         3 x ML3Layer(24||24, learnedge=False) each followed by BatchNorm1d, mean-pool,
                                           fc2(relu(fc1 -> 32)) -> 1
+* ``filtering`` -- filtering.py:252-281    3 x ML3Layer(32||16, learnedge=False) on ONE 900-node grid (supports from the dense
+                                          path of SpectralDesign), no read-out: a per-node regression, fc2 -> 1
 
 The same (unlearned) ``edge_attr2`` feeds every layer; the graph plan (CSR) is built once per batch.  BatchNorm, dropout and
 log-softmax are torch modules (statistics / elementwise work on [N, F] and [B, F], outside the hot path of SURVEY.md 8a).
@@ -33,6 +35,7 @@ MODEL_CONFIGS = {
     "enzymes": dict(nlayer=4, nout1=64, nout2=0, head=(6,), pool="add_max", final="log_softmax", learnedge=False, dropout=0.1,
                     bn="readout", fc_name="fc2"),
     "mutag": dict(nlayer=3, nout1=24, nout2=24, head=(32, 1), pool="mean", final=None, learnedge=False, bn="layers"),
+    "filtering": dict(nlayer=3, nout1=32, nout2=16, head=(1,), pool="none", final=None, learnedge=False, fc_name="fc2"),
 }
 
 
@@ -73,7 +76,8 @@ class GNNML3(nn.Module):
                 x = getattr(self, "bn%d" % (l + 1))(x)
         B = getattr(data, "num_graphs", None)
         pools = {"add": global_add_pool, "mean": global_mean_pool, "max": global_max_pool}
-        x = torch.cat([pools[k](x, data.batch, B) for k in c["pool"].split("_")], 1)
+        if c["pool"] != "none":                          # "none": node-level output (filtering.py:281)
+            x = torch.cat([pools[k](x, data.batch, B) for k in c["pool"].split("_")], 1)
         if c.get("bn") == "readout":
             x = getattr(self, "bn%d" % c["nlayer"])(x)
         prec = _PRECISIONS[self.precision]

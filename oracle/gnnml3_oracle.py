@@ -71,6 +71,8 @@ class OracleGNNML3Variant(torch.nn.Module):
         self.config = config
         if config == "enzymes":
             nout1, nout2, nl = 64, 0, 4
+        elif config == "filtering":                    # filtering.py:252-281: 3 x ML3Layer(32||16, learnedge=False), fc2 per node
+            nout1, nout2, nl = 32, 16, 3
         else:
             nout1, nout2, nl = 24, 24, 3
         nin = nout1 + nout2
@@ -80,6 +82,8 @@ class OracleGNNML3Variant(torch.nn.Module):
         if config == "enzymes":
             self.bn4 = torch.nn.BatchNorm1d(2 * nin)
             self.fc2 = torch.nn.Linear(2 * nin, 6)
+        elif config == "filtering":
+            self.fc2 = torch.nn.Linear(nin, 1)
         else:
             for l in range(nl):
                 setattr(self, "bn%d" % (l + 1), torch.nn.BatchNorm1d(nin))
@@ -94,6 +98,8 @@ class OracleGNNML3Variant(torch.nn.Module):
             x = getattr(self, "conv%d" % (l + 1))(x, ei, ea)
             if self.config == "mutag":
                 x = getattr(self, "bn%d" % (l + 1))(x)
+        if self.config == "filtering":
+            return self.fc2(x)
         if self.config == "enzymes":
             x = torch.cat([global_add_pool(x, b["batch"], b["num_graphs"]), global_max_pool(x, b["batch"], b["num_graphs"])], 1)
             return F.log_softmax(self.fc2(self.bn4(x)), dim=1)

@@ -309,3 +309,48 @@ def test_gnnml3_variants_match_oracle(cfg, train):
         except AssertionError as e:
             bad.append(str(e)[:120])
     assert len(bad) <= 1, bad        # (one tensor may sit on a ReLU / arg-max kink, see _kink_margin)
+
+
+def test_filtering_gnnml3_on_a_grid_designed_by_the_dense_path():
+    """filtering.py:17,252-281: ONE grid graph beyond the shared-memory eigensolver, `SpectralDesign(recfield=5, dv=10,
+    nfreq=10)` (dense device path), 3 x ML3Layer(32||16, learnedge=False), per-node output; forward and parameter gradients
+    against the oracle model fed with the oracle's own supports (K = 11 is odd: the layers run on the two-kernel path)."""
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    from gnn_matlang_b200.models import GNNML3
+    side = 12
+    idx = np.arange(side * side).reshape(side, side)
+    e = np.concatenate([np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()]), np.stack([idx[:-1, :].ravel(), idx[1:, :].ravel()])], 1)
+    ei = np.concatenate([e, e[::-1]], 1)
+    n = side * side
+    kw = dict(recfield=3, dv=10, nfreq=10, adddegree=False)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, 1, generator=g)
+
+    class D(object):
+        pass
+    d = D()
+    d.x, d.edge_index = x.clone(), torch.from_numpy(ei)
+    sd = SpectralDesign(nmax=n, **kw)
+    assert n > sd.max_kernel_nodes()
+    d = sd(d)
+    with np.errstate(all="ignore"):
+        ref_sd = O.spectral_design(ei, x.numpy(), **kw)
+    assert np.array_equal(d.edge_index2.numpy(), ref_sd["edge_index2"])
+    ne = d.edge_attr2.shape[1]
+    torch.manual_seed(11)
+    ref = O.OracleGNNML3Variant("filtering", ne, 1)
+    model = GNNML3("filtering", ne, 1)
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev())
+    ob = dict(x=x, edge_index2=torch.from_numpy(ref_sd["edge_index2"]), edge_attr2=torch.from_numpy(ref_sd["edge_attr2"]))
+    out_r = ref(ob)
+    d.x, d.edge_index2, d.edge_attr2 = d.x.to(dev()), d.edge_index2.to(dev()), d.edge_attr2.to(dev())
+    out = model(d)
+    assert out.shape == (n, 1)
+    assert_close(out, out_r, rtol=1e-4, name="filtering out")          # supports agree to 1e-4 as matrices
+    gout = torch.randn(out_r.shape, generator=g)
+    out_r.backward(gout)
+    out.backward(gout.to(dev()))
+    for (k, p), (_, pr) in zip(model.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, pr.grad, rtol=5e-4, name="grad " + k)
