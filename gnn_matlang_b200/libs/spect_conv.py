@@ -27,6 +27,9 @@ from ..graph import get_plan, sorted_edge_attr
 _PRECISIONS = {"fp32": _lib.PREC_3XTF32, "3xtf32": _lib.PREC_3XTF32, "tf32": _lib.PREC_TF32, "bf16": _lib.PREC_BF16}
 USE_FUSED = os.environ.get("GNNML3_NO_FUSED", "0") != "1"
 USE_LAYER_API = os.environ.get("GNNML3_NO_LAYER_API", "0") != "1"
+# first layer (no gradient w.r.t. x): keep the forward aggregate for the weight gradient (GNNML3_KEEP_AGGREGATE=0 restores the
+# SpMM over the transposed CSR in the backward)
+KEEP_FIRST_LAYER_AGGREGATE = os.environ.get("GNNML3_KEEP_AGGREGATE", "1") != "0"
 
 
 def _use_fused(precision):
@@ -313,10 +316,14 @@ class _ML3LayerFn(torch.autograd.Function):
             xa = ops.aligned_rows(x)
             ws4 = tuple(w.contiguous() for w in (w1, w2, w3, w4)) if fused_edge else None
             gates = (w11.contiguous(), b11.contiguous(), w12.contiguous(), b12.contiguous()) if G > 0 else None
-            y, aux, ea2 = ops.ml3layer_forward(plan, xa, ea_s, ws4, wconv, bconv.contiguous() if bconv is not None else None, gates)
+            # first layer of a model (x carries no gradient, the weights do): the forward also leaves the aggregate behind and the
+            # backward takes dW_k = H_k^T gc from it instead of aggregating S_k^T gc over the transposed CSR
+            keep = (not ctx.needs_input_grad[0]) and ctx.needs_input_grad[6] and Fi <= 32 and KEEP_FIRST_LAYER_AGGREGATE
+            y, aux, ea2, hside = ops.ml3layer_forward(plan, xa, ea_s, ws4, wconv, bconv.contiguous() if bconv is not None else None, gates,
+                                                      keep_aggregate=keep)
             ctx.plan, ctx.fused_edge, ctx.precision, ctx.G = plan, fused_edge, precision, G
             ctx.has_bias, ctx.fused, ctx.composite = bconv is not None, True, True
-            ctx.save_for_backward(xa, ea_s, ea2, y, aux, w1, w2, w3, w4, wconv, w11, w12)
+            ctx.save_for_backward(xa, ea_s, ea2, y, aux, w1, w2, w3, w4, wconv, w11, w12, hside)
             return y
         if fused_edge:
             w1, w2, w3, w4 = w1.contiguous(), w2.contiguous(), w3.contiguous(), w4.contiguous()
@@ -337,7 +344,7 @@ class _ML3LayerFn(torch.autograd.Function):
             y, aux = ops.fused_agg_proj(plan.rowptr, plan.col, None, ea2, xa, wconv.view(K * Fi, Fo), bias=bconv,
                                         S=xa if G > 0 else None, self_mode=1 if G > 0 else 0, Bself=wg, bias_s=bg, G=G,
                                         epilogue=1, win=plan.win, precision=precision)
-            ctx.save_for_backward(xa, ea_s, ea2 if fused_edge else None, y, aux, w1, w2, w3, w4, wconv, w11, w12)
+            ctx.save_for_backward(xa, ea_s, ea2 if fused_edge else None, y, aux, w1, w2, w3, w4, wconv, w11, w12, None)
             return y
         H = _aggregate(plan, ea2, x, K)
         # rows padded to a multiple of 4 floats so that the GEMM epilogues can store 128-bit vectors
@@ -348,12 +355,12 @@ class _ML3LayerFn(torch.autograd.Function):
                 wg = torch.cat([w11.t(), w12.t()], 1).contiguous()
                 ops.gemm_nn(x, wg, torch.cat([b11, b12]), precision=precision, out=pre[:, Fo:])
         y = ops.ml3_act_fwd(pre, Fo, G)
-        ctx.save_for_backward(x, ea_s, ea2 if fused_edge else None, pre, None, w1, w2, w3, w4, wconv, w11, w12)
+        ctx.save_for_backward(x, ea_s, ea2 if fused_edge else None, pre, None, w1, w2, w3, w4, wconv, w11, w12, None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, ea_s, ea2, pre, aux, w1, w2, w3, w4, wconv, w11, w12 = ctx.saved_tensors
+        x, ea_s, ea2, pre, aux, w1, w2, w3, w4, wconv, w11, w12, hside = ctx.saved_tensors
         plan, prec, G = ctx.plan, ctx.precision, ctx.G
         if ea2 is None:
             ea2 = ea_s
@@ -364,7 +371,7 @@ class _ML3LayerFn(torch.autograd.Function):
             gy = gy if gy.stride(1) == 1 else gy.contiguous()
             ws4 = (w1, w2, w3, w4) if ctx.fused_edge else None
             dx, dea, dws, dwc, dbc, dw11, db11, dw12, db12 = ops.ml3layer_backward(
-                plan, x, ea_s, ea2, ws4, wconv, (w11, w12) if G > 0 else None, pre, aux, gy, need[0], need[1], ctx.has_bias)
+                plan, x, ea_s, ea2, ws4, wconv, (w11, w12) if G > 0 else None, pre, aux, gy, need[0], need[1], ctx.has_bias, hside=hside)
             return (dx, dea, dws[0], dws[1], dws[2], dws[3], dwc, dbc, dw11, db11, dw12, db12, None, None, None)
         gy = gy.contiguous()
         Gp = torch.empty(N, K * Fo + 2 * G, dtype=torch.float32, device=x.device)

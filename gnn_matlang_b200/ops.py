@@ -495,9 +495,11 @@ def ml3layer_supported(K, Fi, Fo, G, learnedge):
     return bool(_lib.load().gnnml3_ml3layer_supported(int(K), int(Fi), int(Fo), int(G), int(bool(learnedge))))
 
 
-def ml3layer_forward(plan, x, ea_s, ws4, wconv, bconv, gates):
+def ml3layer_forward(plan, x, ea_s, ws4, wconv, bconv, gates, keep_aggregate=False):
     """Whole ML3Layer forward in one library call (gnnml3_ml3layer_forward).  ``ws4`` = (w1, w2, w3, w4) or None,
-    ``gates`` = (w11, b11, w12, b12) or None.  -> (y [N, Fo+G], aux [N, 2G] | None, ea2 [E, K] | None)"""
+    ``gates`` = (w11, b11, w12, b12) or None.  -> (y [N, Fo+G], aux [N, 2G] | None, ea2 [E, K] | None, hside | None)
+    ``keep_aggregate``: also leave H = [S_0 x .. S_{K-1} x] behind ([N, (K [+1]) * 32]) for a backward that needs the weight
+    gradient but no dx (first layer): dW_k = H_k^T gc then needs no aggregation over the transposed CSR."""
     lib = _lib.load()
     N, Fi = x.shape
     E, K = ea_s.shape
@@ -509,6 +511,8 @@ def ml3layer_forward(plan, x, ea_s, ws4, wconv, bconv, gates):
     ldy = (W + 3) // 4 * 4
     aux = torch.empty(N, 2 * G, dtype=torch.float32, device=dev) if G > 0 else None
     ea2 = torch.empty(E, K, dtype=torch.float32, device=dev) if ws4 is not None else None
+    ldh = (K + (1 if G > 0 else 0)) * 32
+    hside = torch.empty(N, ldh, dtype=torch.float32, device=dev) if (keep_aggregate and Fi <= 32) else None
     ws = _ws(dev, lib.gnnml3_ml3layer_workspace_bytes(N, E, K, Fi, Fo, G), tag="layer")
     p = _lib.ptr
     w = ws4 if ws4 is not None else (None,) * 4
@@ -516,11 +520,11 @@ def ml3layer_forward(plan, x, ea_s, ws4, wconv, bconv, gates):
     with _on(dev):
         _lib.check(lib.gnnml3_ml3layer_forward(p(plan.rowptr), p(plan.col), p(plan.win), N, E, p(x), _ld(x), Fi, p(ea_s), K, p(w[0]), p(w[1]), p(w[2]),
                                                p(w[3]), p(wconv), p(bconv), Fo, p(g[0]), p(g[1]), p(g[2]), p(g[3]), G, p(ea2), p(y), ldy,
-                                               p(aux), p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_forward")
-    return y, aux, ea2
+                                               p(aux), p(hside), ldh, p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_forward")
+    return y, aux, ea2, hside
 
 
-def ml3layer_backward(plan, x, ea_s, ea2, ws4, wconv, gates_w, y, aux, gy, need_dx, need_dea, has_bias):
+def ml3layer_backward(plan, x, ea_s, ea2, ws4, wconv, gates_w, y, aux, gy, need_dx, need_dea, has_bias, hside=None):
     """Whole ML3Layer backward in one library call (gnnml3_ml3layer_backward).
     -> dx, dea, (dw1..dw4), dwconv, dbconv, dw11, db11, dw12, db12 (None where not applicable)"""
     lib = _lib.load()
@@ -547,7 +551,7 @@ def ml3layer_backward(plan, x, ea_s, ea2, ws4, wconv, gates_w, y, aux, gy, need_
             p(plan.rowptr), p(plan.col), p(plan.win), p(plan.rowptrT), p(plan.colT), p(plan.permT), p(plan.winT), N, E, p(x), _ld(x), Fi, p(ea_s), p(ea2), K,
             p(w[0]), p(w[1]), p(w[2]), p(w[3]), p(wconv), Fo, p(gw[0]), p(gw[1]), G, p(y), _ld(y), p(aux), p(gy), _ld(gy),
             int(need_dx), int(need_dea), p(dx), lddx, p(dea), p(dws[0]), p(dws[1]), p(dws[2]), p(dws[3]), p(dwc), p(dbias), p(dw11),
-            p(dw12), p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_backward")
+            p(dw12), p(hside), _ld(hside) if hside is not None else 0, p(ws), ws.numel(), _lib.stream_ptr()), "gnnml3_ml3layer_backward")
     dbc = dbias[:Fo] if has_bias else None
     db11 = dbias[Fo:Fo + G] if G > 0 else None
     db12 = dbias[Fo + G:] if G > 0 else None

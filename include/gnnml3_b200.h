@@ -226,6 +226,10 @@ GNNML3_API int gnnml3_fused_sddmm(const int32_t* rowptr, const int32_t* col, con
  *             outputs ea2 [E,K], y [N, ldy >= Fo+G], aux [N, 2G] (tanh factors, saved for the backward).
  *   backward: gy [N, ldgy]; outputs dx [N, lddx] (if need_dx), dea [E,K] (if need_dea), dw1..dw4, dwconv [K,Fi,Fo],
  *             dbias [Fo + 2G] = (d bconv | d b11 | d b12), dw11/dw12 [G,Fi].
+ *   hside   : optional [N, ldh >= (K [+1 if G > 0]) * 32] (nullable, Fi <= 32).  The forward leaves the aggregate
+ *             H = [S_0 x .. S_{K-1} x] there (support k at column 32 k); a backward that gets it and does not need dx (the first
+ *             layer of a model) takes the weight gradient as dW_k = H_k^T gc in one contraction instead of aggregating
+ *             S_k^T gc over the transposed CSR first.  Pass NULL to both for the plain behaviour.
  * x rows must be 16-byte aligned (ldx % 4 == 0).  gnnml3_ml3layer_supported tells whether a shape is covered.
  * win / winT (nullable) = gnnml3_tile_windows of the dst-sorted / transposed CSR (see gnnml3_fused_agg_proj).
  * --------------------------------------------------------------------------------------------------- */
@@ -235,15 +239,15 @@ GNNML3_API int gnnml3_ml3layer_forward(const int32_t* rowptr, const int32_t* col
                             int Fi, const float* ea_s, int K, const float* w1, const float* w2, const float* w3,
                             const float* w4, const float* wconv, const float* bconv, int Fo, const float* w11,
                             const float* b11, const float* w12, const float* b12, int G, float* ea2, float* y,
-                            int64_t ldy, float* aux, void* workspace, size_t workspace_bytes, void* stream);
+                            int64_t ldy, float* aux, float* hside, int64_t ldh, void* workspace, size_t workspace_bytes, void* stream);
 GNNML3_API int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* col, const int32_t* win, const int32_t* rowptrT,
                              const int32_t* colT, const int32_t* permT, const int32_t* winT, int64_t N, int64_t E, const float* x, int64_t ldx, int Fi,
                              const float* ea_s, const float* ea2, int K, const float* w1, const float* w2, const float* w3,
                              const float* w4, const float* wconv, int Fo, const float* w11, const float* w12, int G,
                              const float* y, int64_t ldy, const float* aux, const float* gy, int64_t ldgy, int need_dx,
                              int need_dea, float* dx, int64_t lddx, float* dea, float* dw1, float* dw2, float* dw3,
-                             float* dw4, float* dwconv, float* dbias, float* dw11, float* dw12, void* workspace,
-                             size_t workspace_bytes, void* stream);
+                             float* dw4, float* dwconv, float* dbias, float* dw11, float* dw12, const float* hside, int64_t ldh,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Readout: PyG global_add_pool (mean = 0) / global_mean_pool (mean = 1) over contiguous node ranges
