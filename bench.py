@@ -652,7 +652,7 @@ def main():
         nbytes = 4.0 * (Nn * Ff + (Nn * Fss if smode == 2 else 0) + Ee * Kk + Ee * (2 if hp else 1) + (Nn + 1) + Kk * Ff * Ncc
                         + Fss * (Nss if smode == 1 else (Ncc if smode == 2 else 0)) + Ncc + Nn * (Ncc + (Gg if smode == 1 else 0))
                         + (Nn * 2 * Gg if smode == 1 else 0))
-        recs.append((msj, nbytes))
+        recs.append((msj, nbytes, "dx" if hp else "forward"))
 
     # ---- roofline of the dominant kernel (the fused aggregate+project layer kernel: forward launches and the transposed
     #      dx launches of the backward)
@@ -675,11 +675,15 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in pk else "fallback 6650",
                     "launches": len(recs), "avg_launch_ms": sp_ms / len(recs), "share_of_step": sp_ms / nprof / eager_ms,
                     "algorithmic_bytes_per_launch": sp_bytes / len(recs),
+                    "by_kind": {k: {"launches": len(v), "avg_launch_ms": sum(r[0] for r in v) / len(v),
+                                    "frac": sum(r[1] for r in v) / (sum(r[0] for r in v) * 1e-3) / 1e9 / peak}
+                                for k, v in (("forward", [r for r in recs if r[2] == "forward"]), ("dx", [r for r in recs if r[2] == "dx"])) if v},
                     "measured_in": "%d steps of the same training step enqueued launch by launch right after the timed region (CUDA "
                                    "events on the launching stream inside gnnml3_fused_agg_proj)" % nprof,
-                    "traffic_note": "mean of 4 forward launches (66 MB each: x / y stay in L2 between kernels) and 3 dx launches (264 MB each: they also "
-                                    "write the 190 MB aggregate side output the weight-gradient contraction reads, which is not credited "
-                                    "as algorithmic bytes); no re-reads",
+                    "traffic_note": "mean of 4 forward launches (66 MB each: x / y stay in L2 between kernels; the first layer's also writes its "
+                                    "aggregate, 218 MB, for the weight gradient) and 3 dx launches (264 MB each: they also "
+                                    "write the 190 MB aggregate side output the weight-gradient contraction reads); the side outputs are not "
+                                    "credited as algorithmic bytes; no re-reads",
                     "note": "latency / hand-off bound, not bandwidth bound: FP32 FMA issue of the aggregation (61 % of the lanes active over ragged "
                             "rows) + per-pass fixed cost (set-up, residuals, tcgen05.st hand-off), see DESIGN.md section 4.1"}
 
