@@ -57,6 +57,8 @@ __global__ void k_unpack_dw(const float* __restrict__ dcat, int K, int Fi, int F
         if (idx < t1) {
             const int o = idx % Fo, i = (idx / Fo) % Fi, k = idx / (Fo * Fi);
             dw[idx] = __ldg(dcat + (int64_t)i * ld + k * pitch + o);
+        } else if (dw11 == nullptr) {
+            // gate weight gradients already written (ml3_act_bwd_y_gw)
         } else if (idx < t1 + t2) {
             const int j = idx - t1, g = j / Fi, i = j % Fi;
             dw11[j] = __ldg(dcat + (int64_t)i * ld + K * pitch + g);
@@ -86,6 +88,11 @@ __global__ void k_unpack_dw_t(const float* __restrict__ ct, const float* __restr
         }
     }
 }
+
+// layer_ops.cu
+int ml3_act_bwd_y_gw(const float* y, int64_t ldy, const float* aux, int64_t ldaux, const float* gy, int64_t ldgy, int64_t N, int Fo, int G,
+                     float* gpre, int64_t ldg, float* colsum, const float* x, int64_t ldx, int Fi, float* dw11, float* dw12,
+                     int* gate_dw_done, void* workspace, size_t workspace_bytes, void* stream);
 
 static inline size_t a256(size_t x) { return align_up(x, 256); }
 
@@ -200,7 +207,13 @@ extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* co
     const int Fo4 = (Fo + 3) / 4 * 4;
     float* gpre = (float*)(ws + w.gpre);
     // d pre = [gc | 0 | g1 g2 | 0] and the three bias gradients (column sums)
-    if ((rc = gnnml3_ml3_act_bwd_y(y, ldy, aux, 2 * G, gy, ldgy, N, Fo, G, gpre, w.ldg, dbias, ws + w.act, w.wT - w.act, stream))) return rc;
+    // (gate width 2: the same two launches also contract the gate gradients with x -> dW11 / dW12; the narrow GEMM below is skipped)
+    int gate_dw_done = 0;
+    const bool hside_form = !need_dx && hside;
+    const bool side_form = need_dx && gnnml3_fused_set_mode(-1) == 0;
+    if ((rc = ml3_act_bwd_y_gw(y, ldy, aux, 2 * G, gy, ldgy, N, Fo, G, gpre, w.ldg, dbias, (hside_form || side_form) ? x : nullptr, ldx, Fi, dw11,
+                               dw12, &gate_dw_done, ws + w.act, w.wT - w.act, stream)))
+        return rc;
     float* wT = (float*)(ws + w.wT);
     float* ws2 = (float*)(ws + w.ws2);
     k_pack_bwd<<<cdiv((int64_t)K * Fo * Fi + 2 * G * Fi, 256), 256, 0, st>>>(wconv, w11, w12, K, Fi, Fo, G, wT, ws2);
@@ -218,10 +231,10 @@ extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* co
         float* cg = dcat + (size_t)Fo * K * 32;             // [Fi, 2G]
         if ((rc = gnnml3_gemm_tn(gpre, w.ldg, hside, ldh, ct, K * 32, N, Fo, K * 32, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream)))
             return rc;
-        if (G > 0 && (rc = gnnml3_gemm_tn(x, ldx, gpre + Fo4, w.ldg, cg, 2 * G, N, Fi, 2 * G, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn,
-                                          stream)))
+        if (G > 0 && !gate_dw_done &&
+            (rc = gnnml3_gemm_tn(x, ldx, gpre + Fo4, w.ldg, cg, 2 * G, N, Fi, 2 * G, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream)))
             return rc;
-        k_unpack_dw_t<<<cdiv((int64_t)K * Fi * Fo + 2 * G * Fi, 256), 256, 0, st>>>(ct, cg, K, Fi, Fo, G, dwconv, dw11, dw12);
+        k_unpack_dw_t<<<cdiv((int64_t)K * Fi * Fo + 2 * G * Fi, 256), 256, 0, st>>>(ct, cg, K, Fi, Fo, gate_dw_done ? 0 : G, dwconv, dw11, dw12);
         GNNML3_LAUNCH_CHECK();
     } else {
     if (need_dx && gnnml3_fused_set_mode(-1) == 0) {          // (the side output exists in the default aggregator mode only)
@@ -252,13 +265,14 @@ extern "C" int gnnml3_ml3layer_backward(const int32_t* rowptr, const int32_t* co
         // K * 32 columns are exactly four 64-wide column tiles of the contraction kernel; the 2G gate columns would open a
         // fifth, almost empty one (+30 % time), so they get their own small contraction straight from d pre
         if ((rc = gnnml3_gemm_tn(x, ldx, Gp, ldG, dcat, ncols, N, Fi, K * 32, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream))) return rc;
-        if ((rc = gnnml3_gemm_tn(x, ldx, gpre + Fo4, w.ldg, dcat + K * 32, ncols, N, Fi, 2 * G, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn,
-                                 stream)))
+        if (!gate_dw_done && (rc = gnnml3_gemm_tn(x, ldx, gpre + Fo4, w.ldg, dcat + K * 32, ncols, N, Fi, 2 * G, GNNML3_PREC_3XTF32, ws + w.tn,
+                                                  w.dcat - w.tn, stream)))
             return rc;
     } else if ((rc = gnnml3_gemm_tn(x, ldx, Gp, ldG, dcat, ncols, N, Fi, ncols, GNNML3_PREC_3XTF32, ws + w.tn, w.dcat - w.tn, stream))) {
         return rc;
     }
-    k_unpack_dw<<<cdiv((int64_t)K * Fi * Fo + 2 * G * Fi, 256), 256, 0, st>>>(dcat, K, Fi, Fo, G, pitch, dwconv, dw11, dw12);
+    k_unpack_dw<<<cdiv((int64_t)K * Fi * Fo + 2 * G * Fi, 256), 256, 0, st>>>(dcat, K, Fi, Fo, G, pitch, dwconv, gate_dw_done ? nullptr : dw11,
+                                                                              gate_dw_done ? nullptr : dw12);
     GNNML3_LAUNCH_CHECK();
     }
     // edge-feature gradient: fused dH + SDDMM, then back through the edge MLP

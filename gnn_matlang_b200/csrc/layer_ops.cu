@@ -185,14 +185,21 @@ k_ml3_act_bwd_y(const float* __restrict__ y, int64_t ldy, const float* __restric
 //   * the column sums accumulate in registers (no shared-memory tile, no second pass over it): shuffle tree over the lanes
 //     that share the group, then the eight warps in fixed order -- deterministic.
 // Same values in gpre bit for bit (same expressions); same per-block partial layout, finished by k_colsum_finish.
-template <int GCV>
+// GW (gate width 2 only): the kernel also contracts the gate gradients with the layer input -- dW11 / dW12 = x^T [g1 | g2], 4 columns
+// against Fi <= 32 -- while the rows are in flight: x adds 128 bytes per row to the stream, the 16 x 4 products per row are free
+// next to the loads, and the separate narrow contraction (k_gemm_tn_narrow + its partial reduction: 25 us per layer on the ZINC
+// step) disappears.  Partials: 128 more columns per block (x column i, gate column g at W2 + 4 i + g), finished by the same
+// launch as the bias sums (k_colsum_finish_gw).
+constexpr int ACTY_GW_COLS = 128;
+template <int GCV, bool GW>
 __global__ void __launch_bounds__(256)
 k_ml3_act_bwd_y_v(const float* __restrict__ y, int64_t ldy, const float* __restrict__ aux, int64_t ldaux,
                   const float* __restrict__ gy, int64_t ldgy, int64_t N, int Fo, int G, float* __restrict__ gpre, int64_t ldg,
-                  float* __restrict__ colpart) {
+                  float* __restrict__ colpart, int pstride, const float* __restrict__ x, int64_t ldx, int Fi) {
     constexpr int RPP = 256 / GCV;                  // rows per pass of the conv block
     constexpr int NPASS = ACTY_ROWS / RPP;          // = GCV / 2
-    __shared__ float red[8][68];
+    __shared__ float red[8][GW ? 132 : 68];
+    __shared__ float4 sgate[GW ? ACTY_ROWS : 1];
     const int Fo4 = 4 * GCV, W2 = Fo + 2 * G;
     const int64_t r0 = (int64_t)blockIdx.x * ACTY_ROWS;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -239,13 +246,21 @@ k_ml3_act_bwd_y_v(const float* __restrict__ y, int64_t ldy, const float* __restr
 #pragma unroll
                     for (int w = 0; w < 8; ++w) v += red[w][t];
                 }
-                colpart[(int64_t)blockIdx.x * W2 + t] = v;
+                colpart[(int64_t)blockIdx.x * pstride + t] = v;
             }
             __syncthreads();
         }
     }
     // ---- gate block: [g1 | g2] at columns Fo4 .. Fo4 + 2G
     if (G == 2) {
+        float4 xr[4];
+        if constexpr (GW) {                          // this thread's 4-column group of the layer input, rows rl + 32 j
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t nx = r0 + (t >> 3) + 32 * j;
+                xr[j] = (nx < N && 4 * (t & 7) < Fi) ? ldg4(x + nx * ldx + 4 * (t & 7)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         const int64_t n = r0 + t;
         if (t < ACTY_ROWS && n < N) {
@@ -257,6 +272,9 @@ k_ml3_act_bwd_y_v(const float* __restrict__ y, int64_t ldy, const float* __restr
             o.w = g1 * tt.y * (1.f - tt.w * tt.w);
             *reinterpret_cast<float4*>(gpre + n * ldg + Fo4) = o;
         }
+        if constexpr (GW) {
+            if (t < ACTY_ROWS) sgate[t] = o;         // zeros for rows beyond N
+        }
         if (colpart) {
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
@@ -267,7 +285,43 @@ k_ml3_act_bwd_y_v(const float* __restrict__ y, int64_t ldy, const float* __restr
             }
             if (lane == 0 && warp < 4) *reinterpret_cast<float4*>(&red[warp][0]) = o;
             __syncthreads();
-            if (t < 4) colpart[(int64_t)blockIdx.x * W2 + Fo + t] = ((red[0][t] + red[1][t]) + red[2][t]) + red[3][t];
+            if (t < 4) colpart[(int64_t)blockIdx.x * pstride + Fo + t] = ((red[0][t] + red[1][t]) + red[2][t]) + red[3][t];
+        }
+        if constexpr (GW) {
+            __syncthreads();                         // sgate complete; red free again
+            float a[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) a[i][g] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 gq = sgate[(t >> 3) + 32 * j];
+                const float xv[4] = {xr[j].x, xr[j].y, xr[j].z, xr[j].w}, gv[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) a[i][g] = fmaf(xv[i], gv[g], a[i][g]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    a[i][g] += __shfl_xor_sync(0xffffffffu, a[i][g], 8);
+                    a[i][g] += __shfl_xor_sync(0xffffffffu, a[i][g], 16);
+                }
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(&red[warp][16 * lane + 4 * i]) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
+            }
+            __syncthreads();
+            if (t < ACTY_GW_COLS) {                  // column t = 4 * (x column) + gate column, fixed order over the warps
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += red[w][t];
+                colpart[(int64_t)blockIdx.x * pstride + W2 + t] = v;
+            }
         }
     } else if (G > 0) {
         // G % 4 == 0, Fo % 4 == 0: GG = G / 2 groups per row (a power of two <= 16), the first G / 4 belong to g1
@@ -304,7 +358,7 @@ k_ml3_act_bwd_y_v(const float* __restrict__ y, int64_t ldy, const float* __restr
                 float v = 0.f;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) v += red[w][t];
-                colpart[(int64_t)blockIdx.x * W2 + Fo + t] = v;
+                colpart[(int64_t)blockIdx.x * pstride + Fo + t] = v;
             }
         }
     }
@@ -320,6 +374,26 @@ __global__ void k_colsum_finish(const float* __restrict__ part, int nblocks, int
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out[c] = s;
+}
+
+// bias sums and gate weight gradients in one finish launch: column c < W2 -> out[c]; column W2 + 4 i + g -> dW11[g][i] (g < 2) or
+// dW12[g - 2][i], x columns i < Fi only
+__global__ void k_colsum_finish_gw(const float* __restrict__ part, int nblocks, int pstride, int W2, int Fi, float* __restrict__ out,
+                                   float* __restrict__ dw11, float* __restrict__ dw12) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= W2 + ACTY_GW_COLS) return;
+    const int j = c - W2, i = j >> 2, g = j & 3;
+    if (c >= W2 && i >= Fi) return;
+    float s = 0.f;
+    for (int b = lane; b < nblocks; b += 32) s += part[(int64_t)b * pstride + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        if (c < W2) { if (out) out[c] = s; }
+        else if (g < 2) dw11[g * Fi + i] = s;
+        else dw12[(g - 2) * Fi + i] = s;
+    }
 }
 
 // one warp per (graph, 32-feature chunk)
@@ -411,7 +485,7 @@ extern "C" int gnnml3_ml3_act_fwd(const float* pre, int64_t ldp, int64_t N, int 
 }
 
 extern "C" size_t gnnml3_ml3_act_bwd_workspace_bytes(int64_t N, int Fo, int G) {
-    return align_up((size_t)cdiv(N > 0 ? N : 1, ACT_ROWS) * (Fo + 2 * G) * sizeof(float), 256);
+    return align_up((size_t)cdiv(N > 0 ? N : 1, ACT_ROWS) * (Fo + 2 * G + 128 /* gate weight-gradient partials */) * sizeof(float), 256);
 }
 
 extern "C" int gnnml3_ml3_act_bwd(const float* pre, int64_t ldp, const float* gy, int64_t ldy, int64_t N, int Fo, int G,
@@ -486,9 +560,31 @@ extern "C" int gnnml3_segment_pool_bwd(const float* gout, const int32_t* graph_p
     return GNNML3_OK;
 }
 
+namespace gnnml3 {
+static int act_bwd_y_impl(const float* y, int64_t ldy, const float* aux, int64_t ldaux, const float* gy, int64_t ldgy, int64_t N, int Fo,
+                          int G, float* gpre, int64_t ldg, float* colsum, const float* x, int64_t ldx, int Fi, float* dw11, float* dw12,
+                          int* gate_dw_done, void* workspace, size_t workspace_bytes, void* stream_);
+// layer_api.cu: d pre + bias sums and, when the shape allows (gate width 2, Fi <= 32, aligned x, N > 0), the gate weight gradients
+// dW11 / dW12 [G, Fi] in the same two launches; *gate_dw_done tells the caller whether they were written
+int ml3_act_bwd_y_gw(const float* y, int64_t ldy, const float* aux, int64_t ldaux, const float* gy, int64_t ldgy, int64_t N, int Fo, int G,
+                     float* gpre, int64_t ldg, float* colsum, const float* x, int64_t ldx, int Fi, float* dw11, float* dw12,
+                     int* gate_dw_done, void* workspace, size_t workspace_bytes, void* stream) {
+    return act_bwd_y_impl(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, colsum, x, ldx, Fi, dw11, dw12, gate_dw_done, workspace,
+                          workspace_bytes, stream);
+}
+}  // namespace gnnml3
+
 extern "C" int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* aux, int64_t ldaux, const float* gy, int64_t ldgy,
                                     int64_t N, int Fo, int G, float* gpre, int64_t ldg, float* colsum, void* workspace,
                                     size_t workspace_bytes, void* stream_) {
+    return gnnml3::act_bwd_y_impl(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, colsum, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                  workspace, workspace_bytes, stream_);
+}
+
+static int gnnml3::act_bwd_y_impl(const float* y, int64_t ldy, const float* aux, int64_t ldaux, const float* gy, int64_t ldgy, int64_t N,
+                                  int Fo, int G, float* gpre, int64_t ldg, float* colsum, const float* x, int64_t ldx, int Fi,
+                                  float* dw11, float* dw12, int* gate_dw_done, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (gate_dw_done) *gate_dw_done = 0;
     GNNML3_REQUIRE(N >= 0 && Fo >= 1 && G >= 0, "ml3_act_bwd_y: bad shape");
     cudaStream_t st = (cudaStream_t)stream_;
     if (N == 0) {
@@ -514,13 +610,28 @@ extern "C" int gnnml3_ml3_act_bwd_y(const float* y, int64_t ldy, const float* au
                           (G % 4 == 0 && (G & (G - 1)) == 0 && G <= 32 && Fo % 4 == 0 && ldaux % 4 == 0 && ((uintptr_t)aux & 15) == 0);
     static const bool general_only = [] { const char* e = getenv("GNNML3_ACT_GENERAL"); return e && e[0] == '1'; }();   // measurement switch
     const bool fast = !general_only && vec_in && gates_ok && ldg == Fo4 + 2 * G && (Fo4 == 16 || Fo4 == 32 || Fo4 == 64) && ldy >= Fo4 && ldgy >= Fo4;
-    if (fast && Fo4 == 16) k_ml3_act_bwd_y_v<4><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part);
-    else if (fast && Fo4 == 32) k_ml3_act_bwd_y_v<8><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part);
-    else if (fast) k_ml3_act_bwd_y_v<16><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part);
+    const int W2 = Fo + 2 * G;
+    static const bool no_gw = [] { const char* e = getenv("GNNML3_ACT_NO_GATE_DW"); return e && e[0] == '1'; }();      // measurement switch
+    const bool gw = fast && !no_gw && G == 2 && x && dw11 && dw12 && part && Fi >= 1 && Fi <= 32 && ldx % 4 == 0 && ldx >= (Fi + 3) / 4 * 4 &&
+                    ((uintptr_t)x & 15) == 0;
+    if (gw) {
+        const int ps = W2 + ACTY_GW_COLS;
+        if (Fo4 == 16) k_ml3_act_bwd_y_v<4, true><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, ps, x, ldx, Fi);
+        else if (Fo4 == 32) k_ml3_act_bwd_y_v<8, true><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, ps, x, ldx, Fi);
+        else k_ml3_act_bwd_y_v<16, true><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, ps, x, ldx, Fi);
+        GNNML3_LAUNCH_CHECK();
+        k_colsum_finish_gw<<<cdiv(ps, 8), 256, 0, st>>>(part, nb, ps, W2, Fi, colsum, dw11, dw12);
+        GNNML3_LAUNCH_CHECK();
+        if (gate_dw_done) *gate_dw_done = 1;
+        return GNNML3_OK;
+    }
+    if (fast && Fo4 == 16) k_ml3_act_bwd_y_v<4, false><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, W2, nullptr, 0, 0);
+    else if (fast && Fo4 == 32) k_ml3_act_bwd_y_v<8, false><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, W2, nullptr, 0, 0);
+    else if (fast) k_ml3_act_bwd_y_v<16, false><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, W2, nullptr, 0, 0);
     else k_ml3_act_bwd_y<<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, vec_in);
     GNNML3_LAUNCH_CHECK();
     if (colsum) {
-        k_colsum_finish<<<cdiv(Fo + 2 * G, 8), 256, 0, st>>>(part, nb, Fo + 2 * G, colsum);
+        k_colsum_finish<<<cdiv(W2, 8), 256, 0, st>>>(part, nb, W2, colsum);
         GNNML3_LAUNCH_CHECK();
     }
     return GNNML3_OK;
