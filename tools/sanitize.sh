@@ -18,3 +18,13 @@ echo "memcheck (device collation, SpectralDesign, config 3) exit code: $?"
 timeout 300 compute-sanitizer --tool racecheck --error-exitcode 7 \
     python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -x -k "(edge_mlp or gemm_tn or segment_pool) and not 70000 and $SEL"
 echo "racecheck exit code: $?"
+# last session of round 2: streaming act_bwd_y (+ gate weight gradients), 32-lane partial reduction, first-layer aggregate form,
+# aligned_rows copy, dense SpectralDesign path
+if [ "${SANITIZE_LATE:-1}" = "1" ]; then
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 7 \
+    python -m pytest tests/test_gpu_z_added_late.py tests/test_gpu_modules.py -q -x -k "(act_bwd or aligned_rows or whole_layer or column_block) and not 40000 and $SEL"
+echo "memcheck (late kernels) exit code: $?"
+timeout 300 compute-sanitizer --tool racecheck --error-exitcode 7 \
+    python -m pytest tests/test_gpu_z_added_late.py tests/test_gpu_fused.py -q -x -k "act_bwd and $SEL"
+echo "racecheck (act_bwd_y kernels) exit code: $?"
+fi
