@@ -378,18 +378,22 @@ __global__ void k_colsum_finish(const float* __restrict__ part, int nblocks, int
 
 // bias sums and gate weight gradients in one finish launch: column c < W2 -> out[c]; column W2 + 4 i + g -> dW11[g][i] (g < 2) or
 // dW12[g - 2][i], x columns i < Fi only
-__global__ void k_colsum_finish_gw(const float* __restrict__ part, int nblocks, int pstride, int W2, int Fi, float* __restrict__ out,
-                                   float* __restrict__ dw11, float* __restrict__ dw12) {
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= W2 + ACTY_GW_COLS) return;
+__global__ void __launch_bounds__(128)
+k_colsum_finish_gw(const float* __restrict__ part, int nblocks, int pstride, int W2, int Fi, float* __restrict__ out,
+                   float* __restrict__ dw11, float* __restrict__ dw12) {
+    // one BLOCK per column (one warp per column walked ~46 dependent-free but serial loads per lane: 10 us per launch)
+    __shared__ float red[4];
+    const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = c - W2, i = j >> 2, g = j & 3;
     if (c >= W2 && i >= Fi) return;
     float s = 0.f;
-    for (int b = lane; b < nblocks; b += 32) s += part[(int64_t)b * pstride + c];
+    for (int b = threadIdx.x; b < nblocks; b += 128) s += part[(int64_t)b * pstride + c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = (red[0] + red[1]) + (red[2] + red[3]);
         if (c < W2) { if (out) out[c] = s; }
         else if (g < 2) dw11[g * Fi + i] = s;
         else dw12[(g - 2) * Fi + i] = s;
@@ -620,7 +624,7 @@ static int gnnml3::act_bwd_y_impl(const float* y, int64_t ldy, const float* aux,
         else if (Fo4 == 32) k_ml3_act_bwd_y_v<8, true><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, ps, x, ldx, Fi);
         else k_ml3_act_bwd_y_v<16, true><<<nb, 256, 0, st>>>(y, ldy, aux, ldaux, gy, ldgy, N, Fo, G, gpre, ldg, part, ps, x, ldx, Fi);
         GNNML3_LAUNCH_CHECK();
-        k_colsum_finish_gw<<<cdiv(ps, 8), 256, 0, st>>>(part, nb, ps, W2, Fi, colsum, dw11, dw12);
+        k_colsum_finish_gw<<<ps, 128, 0, st>>>(part, nb, ps, W2, Fi, colsum, dw11, dw12);
         GNNML3_LAUNCH_CHECK();
         if (gate_dw_done) *gate_dw_done = 1;
         return GNNML3_OK;
