@@ -223,6 +223,41 @@ def test_launch_list_summary_matches_the_committed_profile():
     assert any("k_fused_agg_proj" in l for l in out.splitlines()[1:3])            # the dominant kernel the roofline is quoted on
 
 
+def test_round2_launch_list_and_bench_line_are_consistent():
+    """The committed round-2 evidence hangs together: the one-step kernel table is tools/summarise_launches.py applied to the
+    committed raw ncu launch list (a step starts at k_csr_hist), the bench line carries every key of the contract, its roofline
+    fraction is achieved / peak for the kernel that leads the launch list, the kernel shares it quotes are the table's, and the
+    kernel time of the list fits the measured step (cold-cache, serialised: within 10 %)."""
+    import json
+    raw = os.path.join(ROOT, "profiles", "r02_ncu_launches_zinc_final_raw.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarise_launches.py"), raw, "--marker", "k_csr_hist"],
+                         capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(ROOT, "profiles", "r02_ncu_launches_zinc_one_step_final.csv")).read()
+    rows = [l.rsplit(",", 3) for l in out.strip().splitlines()[1:]]
+    assert rows[-1][0] == "TOTAL" and abs(sum(float(r[-1]) for r in rows[:-1]) - 1.0) < 5e-3
+    assert "k_fused_ts" in rows[0][0]
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_final_zinc_b8192.json")))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["config"]["workload"] == "zinc" and d["vs_baseline"] is None and d["higher_is_better"] is True
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and "k_fused_ts" in rf["kernel"]
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert abs(rf["peak"] - json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) < 1e-6
+    g = d["config"]["graphs_per_step_all_gpus"]
+    assert abs(d["value"] - g / (d["ms_per_step"] * 1e-3)) < 1e-3 * d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] <= d["value"] * 1.02
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["gpu_launches"] == d["gpu_launches_per_step"] * d["steps"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    total_us = float(rows[-1][2])
+    assert abs(total_us * 1e-3 - d["ms_per_step"]) < 0.1 * d["ms_per_step"]
+    top = d["kernel_shares_one_step"]["kernels"]
+    name0 = rows[0][0].strip('"')
+    assert name0 in top and abs(top[name0]["share"] - float(rows[0][-1])) < 1e-3
+
+
 def test_compact_wire_format_round_trip_and_device_dataset_on_cpu():
     """batch.CompactBatch (host -> device wire format): the host-side conversion is exact and reversible (numpy restatement of
     the device expansion); the expansion / collation themselves are library kernels since round 2 and refuse CPU tensors (the
