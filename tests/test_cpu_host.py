@@ -307,3 +307,29 @@ def test_shard_graphs_balances_by_size_not_by_count():
         assert by_count.max() / by_count.mean() > 1.3                                        # what equal counts would give
         assert shard_graphs(sizes, world, rank=1) == r[1]
     assert shard_graphs([5], 4) == [(0, 0), (0, 0), (0, 1), (1, 1)] or sum(b - a for a, b in shard_graphs([5], 4)) == 1
+
+
+def test_spectral_design_envelope_and_no_cpu_fallback_for_large_graphs():
+    """The shared-memory eigensolver's envelope is a host-side query; graphs beyond it take the dense DEVICE path, which -- like
+    the rest of the product -- refuses to compute on a machine without CUDA instead of falling back to the CPU."""
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    sd = SpectralDesign(recfield=5, dv=10, nfreq=10)
+    lim = sd.max_kernel_nodes()
+    assert 64 <= lim <= 128
+    assert SpectralDesign(nfreq=5).max_kernel_nodes() >= lim            # fewer supports leave more shared memory for the matrix
+    if not torch.cuda.is_available():
+        n = lim + 50
+        ei = np.vstack((np.arange(n - 1), np.arange(1, n)))
+        with pytest.raises(RuntimeError, match="CUDA"):
+            sd._design_large(np.concatenate([ei, ei[::-1]], 1), n)
+
+
+def test_filtering_variant_has_the_reference_parameter_names():
+    """filtering.py:252-281: conv1..conv3 = ML3Layer(learnedge=False) (fc1_1..fc1_4 absent, conv1, fc11, fc12), then fc2 -- the
+    product model and the oracle restatement expose the same state_dict keys in the same (creation) order."""
+    from gnn_matlang_b200.models import GNNML3
+    from oracle import gnnml3_oracle as O
+    keys = [k for k, _ in GNNML3("filtering", 11, 1).named_parameters()]
+    assert keys == [k for k, _ in O.OracleGNNML3Variant("filtering", 11, 1).named_parameters()]
+    assert keys[:6] == ["conv1.conv1.weight", "conv1.conv1.bias", "conv1.fc11.weight", "conv1.fc11.bias", "conv1.fc12.weight", "conv1.fc12.bias"]
+    assert keys[-2:] == ["fc2.weight", "fc2.bias"] and len(keys) == 3 * 6 + 2
