@@ -139,6 +139,19 @@ def main():
     add_case("directed", ei_dir, exp_list[5].x.numpy().astype(np.float32), **kw_g8)
     add_case("no_edges", np.zeros((2, 0), np.int64), np.ones((3, 1), np.float32), **kw_g8)
     add_case("single_node", np.zeros((2, 0), np.int64), np.ones((1, 1), np.float32), **kw_g8)
+    # graphs beyond the shared-memory eigensolver of the CUDA path (2-D grids as in filtering.py:17, small enough for a fixture):
+    # the product designs them on its dense device path.  (No draws from `rng`: the fixtures above and below stay byte-identical.)
+
+    def grid(side):
+        idx = np.arange(side * side).reshape(side, side)
+        e = np.concatenate([np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()]), np.stack([idx[:-1, :].ravel(), idx[1:, :].ravel()])], 1)
+        return side * side, np.concatenate([e, e[::-1]], 1)
+    n, ei = grid(12)
+    add_case("grid12_filtering", ei, np.ones((n, 1), np.float32), recfield=3, dv=10, nfreq=10, adddegree=False)   # filtering.py:17 (recfield 5 there)
+    n, ei = grid(14)
+    add_case("grid14_degree_adj", ei, np.ones((n, 1), np.float32), recfield=2, dv=5, nfreq=5, adddegree=True, addadj=True)
+    n, ei = grid(13)
+    add_case("grid13_adjacency_spectrum", ei, np.ones((n, 2), np.float32), recfield=1, dv=2, nfreq=4, laplacien=False, vmax=3.0)
 
     blob = {}
     import json
