@@ -297,6 +297,32 @@ def main():
     blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(OUT, "spect_concat.npz"), **blob)
 
+    # ------------------------------------------------------------------ filtering.py GNNML3 (filtering.py:252-281) on a grid
+    # 3 x ML3Layer(learnedge=False, 32||16) + fc2 per node, supports = the grid12_filtering case above (own file, own seed)
+    c12 = [c for c in cases if c["name"] == "grid12_filtering"][0]
+    ne_f = c12["ea2"].shape[1]
+
+    class RefFiltering(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = ref_conv.ML3Layer(learnedge=False, nedgeinput=ne_f, nedgeoutput=ne_f, ninp=1, nout1=32, nout2=16)
+            self.conv2 = ref_conv.ML3Layer(learnedge=False, nedgeinput=ne_f, nedgeoutput=ne_f, ninp=48, nout1=32, nout2=16)
+            self.conv3 = ref_conv.ML3Layer(learnedge=False, nedgeinput=ne_f, nedgeoutput=ne_f, ninp=48, nout1=32, nout2=16)
+            self.fc2 = torch.nn.Linear(48, 1)
+
+    torch.manual_seed(2)
+    fm = RefFiltering()
+    xf = torch.randn(c12["ox"].shape[0], 1)
+    ei_f, ea_f = torch.as_tensor(c12["ei2"]), torch.as_tensor(c12["ea2"])
+    out_f = fm.fc2(fm.conv3(fm.conv2(fm.conv1(xf, ei_f, ea_f), ei_f, ea_f), ei_f, ea_f))
+    gout_f = torch.randn_like(out_f)
+    out_f.backward(gout_f)
+    blob = {"x": xf.numpy(), "out": out_f.detach().numpy(), "gout": gout_f.numpy()}
+    for k, v in fm.named_parameters():
+        blob["p/" + k] = v.detach().numpy()
+        blob["g/" + k] = v.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "filtering_model.npz"), **blob)
+
     print("params:", sum(p.numel() for p in model.parameters()))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -354,3 +354,29 @@ def test_filtering_gnnml3_on_a_grid_designed_by_the_dense_path():
     out.backward(gout.to(dev()))
     for (k, p), (_, pr) in zip(model.named_parameters(), ref.named_parameters()):
         assert_close(p.grad, pr.grad, rtol=5e-4, name="grad " + k)
+
+
+def test_filtering_gnnml3_matches_the_reference_fixture():
+    """The same model against the fixture made by the UNMODIFIED reference (tests/golden/filtering_model.npz: 12x12 grid, reference
+    SpectralDesign supports, seed-2 weights): supports rebuilt here on the dense device path, forward and every parameter
+    gradient through the CUDA layers."""
+    from gnn_matlang_b200.libs.utils import SpectralDesign
+    from gnn_matlang_b200.models import GNNML3
+    z, _ = load_npz("filtering_model.npz")
+    sdz, _ = load_npz("spectral_design.npz")
+
+    class D(object):
+        pass
+    d = D()
+    d.x, d.edge_index = torch.tensor(z["x"]), torch.tensor(sdz["grid12_filtering/ei"])
+    d = SpectralDesign(nmax=144, recfield=3, dv=10, nfreq=10, adddegree=False)(d)
+    assert np.array_equal(d.edge_index2.numpy(), sdz["grid12_filtering/ei2"])
+    model = GNNML3("filtering", d.edge_attr2.shape[1], 1)
+    model.load_state_dict({k[2:]: torch.tensor(z[k]) for k in z.files if k.startswith("p/")})
+    model = model.to(dev())
+    d.x, d.edge_index2, d.edge_attr2 = d.x.to(dev()), d.edge_index2.to(dev()), d.edge_attr2.to(dev())
+    out = model(d)
+    assert_close(out, torch.tensor(z["out"]), rtol=1e-4, name="filtering out vs reference fixture")
+    out.backward(torch.tensor(z["gout"]).to(dev()))
+    for k, p in model.named_parameters():
+        assert_close(p.grad, torch.tensor(z["g/" + k]), rtol=5e-4, name="grad " + k)

@@ -106,6 +106,22 @@ def test_graph8c_model_fixture():
     np.testing.assert_allclose(emb.numpy(), z["emb"], rtol=1e-5, atol=1e-6)
 
 
+def test_filtering_model_fixture():
+    """filtering.py:252-281 built from the UNMODIFIED reference's `ML3Layer(learnedge=False)` on a 12x12 grid (supports: the
+    grid12_filtering SpectralDesign fixture): the oracle model reproduces the per-node output and every parameter gradient."""
+    z, _ = load_npz("filtering_model.npz")
+    ei2, ea2 = SD_Z["grid12_filtering/ei2"], SD_Z["grid12_filtering/ea2"]
+    model = O.OracleGNNML3Variant("filtering", ea2.shape[1], 1)
+    assert [k for k, _ in model.named_parameters()] == [k[2:] for k in z.files if k.startswith("p/")]       # names and creation order
+    model.load_state_dict({k[2:]: torch.tensor(z[k]) for k in z.files if k.startswith("p/")})
+    out = model(dict(x=torch.tensor(z["x"]), edge_index2=torch.tensor(ei2), edge_attr2=torch.tensor(ea2)))
+    np.testing.assert_allclose(out.detach().numpy(), z["out"], rtol=1e-5, atol=1e-6)
+    out.backward(torch.tensor(z["gout"]))
+    for k, p in model.named_parameters():
+        g = z["g/" + k]
+        np.testing.assert_allclose(p.grad.numpy(), g, rtol=1e-4, atol=1e-5 * np.abs(g).max())
+
+
 def test_graph8c_isomorphism_kat():
     """The reference's own known-answer run (graph8c.py:281-302): embed all 11,117 graphs with freshly initialised models
     (``torch.manual_seed(iter)``), mark a pair distinguished when its L1 embedding distance exceeds 1e-3 under any seed so
